@@ -1,0 +1,156 @@
+/*
+ * sgr.h — C ABI of the B200-native differentiable Gaussian rasterizer (libsgr.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of zju3dv/street_gaussians that this repository
+ * replaces.  Each entry point names the reference interface it stands in for
+ * (paths relative to /root/reference/submodules/diff-gaussian-rasterization = "DGR/",
+ *  /root/reference/submodules/simple-knn = "KNN/").
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only; no torch / C++ types cross this boundary.
+ *  - every pointer is a DEVICE pointer unless it is documented as host; all fp32 arrays are contiguous
+ *    and laid out exactly like the tensors of the reference Python API
+ *    (DGR/diff_gaussian_rasterization/__init__.py:197-233): means3D[P,3], shs[P,M,3], colors_precomp[P,3],
+ *    semantics[P,S], opacities[P,1], scales[P,3], rotations[P,4] (w,x,y,z), cov3D_precomp[P,6],
+ *    images [C,H,W].  A NULL pointer plays the role of the reference's empty tensor.
+ *  - the CALLER owns all memory, including the forward->backward state buffers and scratch; the library is
+ *    stateless between calls, re-entrant and thread-safe; every kernel is enqueued on `stream` (a cudaStream_t
+ *    passed as void*).  The only host synchronisation is one 8-byte read-back of the instance count inside
+ *    sgr_forward (the reference has the same one at DGR/cuda_rasterizer/rasterizer_impl.cu:283-284).
+ *  - return value: 0 on success, negative SGR_E* on failure; sgr_last_error() returns a thread-local message.
+ *    With frame.debug != 0 every launch is followed by a stream synchronise + error check
+ *    (the reference's CHECK_CUDA, DGR/cuda_rasterizer/auxiliary.h:166-173).
+ */
+#ifndef SGR_H_INCLUDED
+#define SGR_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGR_ABI_VERSION 1
+
+#define SGR_OK 0
+#define SGR_EINVAL (-1)   /* bad argument combination / shape                     */
+#define SGR_ECUDA (-2)    /* a CUDA runtime call or kernel failed                  */
+#define SGR_ENOMEM (-3)   /* caller-provided buffer too small / allocator failed  */
+#define SGR_EUNSUPPORTED (-4)
+
+/* Maximum number of extra feature ("semantic") channels the BACKWARD pass accepts.  The reference has a
+ * compile-time cap NUM_CLASSES = 20 (DGR/cuda_rasterizer/config.h:16) beyond which it is undefined behaviour;
+ * this library returns SGR_EUNSUPPORTED above SGR_MAX_SEMANTIC_BWD instead.  Forward accepts any S. */
+#define SGR_MAX_SEMANTIC_BWD 32
+
+/* Per-call frame description == the 12 fields of GaussianRasterizationSettings
+ * (DGR/diff_gaussian_rasterization/__init__.py:167-179) + problem sizes + the tile-row band this process owns. */
+typedef struct SgrFrame {
+	int32_t P;              /* number of Gaussians                                                       */
+	int32_t D;              /* active SH degree (settings.sh_degree)                                     */
+	int32_t M;              /* SH coefficients per Gaussian as stored (shs.shape[1]); 0 with colors_precomp */
+	int32_t S;              /* extra feature channels (semantics.shape[1])                               */
+	int32_t width, height;  /* image_width, image_height                                                 */
+	float tan_fovx, tan_fovy;
+	float scale_modifier;
+	int32_t prefiltered;    /* accepted for API parity; a culled point is simply skipped (the reference traps) */
+	int32_t debug;
+	/* Multi-GPU tile-row sharding (no reference counterpart): this call rasterises only the
+	 * 16-pixel tile rows r with row_begin <= r < row_end and (r - row_begin) % row_step == 0.
+	 * {0, 0, 0} or {0, ceil(H/16), 1} means the whole image.  Pixels of other rows are left untouched. */
+	int32_t row_begin, row_end, row_step;
+	const float *bg;         /* [3]  device                                                              */
+	const float *viewmatrix; /* [16] device: world_view_transform  (W2C transposed, row-major)           */
+	const float *projmatrix; /* [16] device: full_proj_transform                                         */
+	const float *campos;     /* [3]  device                                                              */
+} SgrFrame;
+
+/* Caller-supplied device allocator, called at most once per sgr_forward with the size of the binning state once the
+ * instance count is known.  Stands in for the reference's resize callbacks (std::function<char*(size_t)>,
+ * DGR/rasterize_points.cu:27-33, DGR/cuda_rasterizer/rasterizer.h:36-38).  Must return a 256-byte aligned device
+ * pointer valid until the matching sgr_backward_* calls have been enqueued, or NULL on failure. */
+typedef void *(*sgr_alloc_fn)(void *user, size_t nbytes);
+
+int sgr_abi_version(void);
+const char *sgr_last_error(void);
+
+/* Sizes (bytes) of the caller-owned forward state.  geom: per-Gaussian records (reference GeometryState,
+ * DGR/cuda_rasterizer/rasterizer_impl.h:21-37); img: per-pixel / per-tile state (ImageState, :46-52).
+ * binning (BinningState, :54-64) depends on the instance count R and is requested through sgr_alloc_fn;
+ * sgr_binning_bytes(R) reports what will be asked for. */
+int sgr_state_sizes(const SgrFrame *frame, size_t *geom_bytes, size_t *img_bytes);
+size_t sgr_binning_bytes(int64_t num_instances);
+
+/* Forward rasterisation.  Replaces RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward
+ * (DGR/rasterize_points.cu:35-124, DGR/cuda_rasterizer/rasterizer_impl.cu:197-343; pybind name
+ * `rasterize_gaussians`, DGR/ext.cpp:16).
+ *   exactly one of (shs, colors_precomp) and exactly one of ((scales, rotations), cov3D_precomp) must be non-NULL.
+ *   out_color[3,H,W], out_depth[1,H,W], out_alpha[1,H,W], out_semantic[S,H,W] (may be NULL when S == 0), radii[P]:
+ *   every element of the owned tile rows is written (no pre-zeroing needed for a whole-image band); radii is
+ *   always fully written.
+ *   *binning_state receives the pointer obtained from `alloc`; *num_instances the (Gaussian, tile) instance count
+ *   of THIS library's binning (exact opacity-aware tile culling makes it <= the reference's num_rendered). */
+int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                const float *semantics, const float *opacities, const float *scales, const float *rotations,
+                const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
+                int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
+                void *alloc_user, void **binning_state, int64_t *num_instances, void *stream);
+
+/* Backward, stage 1 of 2: per-pixel backward blend.  Replaces BACKWARD::render
+ * (DGR/cuda_rasterizer/backward.cu:415-641, called at rasterizer_impl.cu:454-477).
+ *   grad2d[P,12] receives the per-Gaussian screen-space sums
+ *     [0..2] dL/dmean2D (x, y NDC-scaled; z = sum |x|+|y|), [3..5] dL/dconic (xx, xy, yy), [6] dL/dopacity,
+ *     [7..9] dL/dcolor, [10] dL/ddepth, [11] unused
+ *   and dL_dsemantics[P,S] the feature-channel sums.  Both are ZEROED by this call and then accumulated, so with
+ *   tile-row sharding each rank holds a partial sum that must be summed across ranks (one all-reduce) before
+ *   stage 2.  S must be <= SGR_MAX_SEMANTIC_BWD. */
+int sgr_backward_blend(const SgrFrame *frame, int64_t num_instances, const float *semantics, const void *geom_state,
+                       const void *binning_state, const void *img_state, const float *out_alpha, const float *dL_dcolor,
+                       const float *dL_ddepth, const float *dL_dalpha, const float *dL_dsemantic, float *grad2d,
+                       float *dL_dsemantics, void *stream);
+
+/* Backward, stage 2 of 2: per-Gaussian chain rule.  Replaces BACKWARD::preprocess = computeCov2DCUDA + preprocessCUDA
+ * (DGR/cuda_rasterizer/backward.cu:643-709, 144-274, 346-412).  Every element of every non-NULL output is written
+ * (zeros for Gaussians with radii <= 0), so outputs need no pre-zeroing:
+ *   dL_dmeans3D[P,3], dL_dmeans2D[P,3], dL_dsh[P,M,3] (NULL when colors_precomp), dL_dcolors_precomp[P,3] (NULL with SH),
+ *   dL_dopacity[P,1], dL_dscales[P,3], dL_drotations[P,4] (NULL with cov3D_precomp), dL_dcov3D[P,6] (may be NULL). */
+int sgr_backward_geom(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                      const float *scales, const float *rotations, const float *cov3D_precomp, const int32_t *radii,
+                      const void *geom_state, const float *grad2d, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh,
+                      float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                      float *dL_dcov3D, void *stream);
+
+/* Convenience: stage 1 + stage 2 on one device.  Replaces RasterizeGaussiansBackwardCUDA ->
+ * CudaRasterizer::Rasterizer::backward (DGR/rasterize_points.cu:126-220, rasterizer_impl.cu:396-506; pybind name
+ * `rasterize_gaussians_backward`, DGR/ext.cpp:17).  grad2d_scratch is P*12 floats of caller scratch. */
+int sgr_backward(const SgrFrame *frame, int64_t num_instances, const float *means3D, const float *shs,
+                 const float *colors_precomp, const float *semantics, const float *scales, const float *rotations,
+                 const float *cov3D_precomp, const int32_t *radii, const void *geom_state, const void *binning_state,
+                 const void *img_state, const float *out_alpha, const float *dL_dcolor, const float *dL_ddepth,
+                 const float *dL_dalpha, const float *dL_dsemantic, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh,
+                 float *dL_dcolors_precomp, float *dL_dsemantics, float *dL_dopacity, float *dL_dscales,
+                 float *dL_drotations, float *dL_dcov3D, float *grad2d_scratch, void *stream);
+
+/* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
+ * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */
+int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,
+                     void *stream);
+
+/* radii[P] and means2D[P,2] only.  Replaces RasterizeGaussiansfilterCUDA -> Rasterizer::visible_filter ->
+ * filter_preprocessCUDA (DGR/rasterize_points.cu:243-307, rasterizer_impl.cu:345-392, forward.cu:259-334;
+ * pybind `rasterize_gaussians_filter`, DGR/ext.cpp:19).  Both outputs are fully written (zeros when culled). */
+int sgr_visible_filter(const SgrFrame *frame, const float *means3D, const float *scales, const float *rotations,
+                       const float *cov3D_precomp, int32_t *radii, float *means2D, void *stream);
+
+/* mean squared distance to the 3 nearest neighbours.  Replaces distCUDA2 -> SimpleKNN::knn
+ * (KNN/spatial.cu:14-26, KNN/simple_knn.cu:185-220; pybind `distCUDA2`, KNN/ext.cpp:15-17).
+ * scratch: sgr_knn_scratch_bytes(P) bytes of caller scratch. */
+size_t sgr_knn_scratch_bytes(int32_t P);
+int sgr_knn_mean_dist2(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGR_H_INCLUDED */

@@ -1,0 +1,79 @@
+"""ctypes loader for libsgr.so (include/sgr.h).  The product path has NO fallback: if the CUDA library is missing or
+does not export the ABI, importing / calling raises — it never routes through a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsgr.so")
+ABI_VERSION = 1
+
+SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_state_sizes", "sgr_binning_bytes", "sgr_forward", "sgr_backward_blend",
+           "sgr_backward_geom", "sgr_backward", "sgr_mark_visible", "sgr_visible_filter", "sgr_knn_scratch_bytes",
+           "sgr_knn_mean_dist2"]
+
+
+class SgrFrame(C.Structure):
+    _fields_ = [("P", C.c_int32), ("D", C.c_int32), ("M", C.c_int32), ("S", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float), ("prefiltered", C.c_int32),
+                ("debug", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_step", C.c_int32),
+                ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p)]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+_lib = None
+
+
+class SgrError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libsgr.so (once).  Raises if the extension has not been built — there is deliberately no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SgrError(f"{LIB_PATH} not found: build it with `python -m street_gaussians_b200.build` "
+                       "(or __graft_entry__.build()); street_gaussians_b200 has no non-CUDA fallback")
+    L = C.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        if not hasattr(L, s):
+            raise SgrError(f"libsgr.so does not export {s}")
+    L.sgr_abi_version.restype = C.c_int
+    if L.sgr_abi_version() != ABI_VERSION:
+        raise SgrError(f"libsgr.so ABI version {L.sgr_abi_version()} != expected {ABI_VERSION}; rebuild")
+    L.sgr_last_error.restype = C.c_char_p
+    L.sgr_state_sizes.restype = C.c_int
+    L.sgr_state_sizes.argtypes = [C.POINTER(SgrFrame), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.sgr_binning_bytes.restype = C.c_size_t
+    L.sgr_binning_bytes.argtypes = [C.c_int64]
+    vp = C.c_void_p
+    L.sgr_forward.restype = C.c_int
+    L.sgr_forward.argtypes = [C.POINTER(SgrFrame)] + [vp] * 8 + [vp] * 5 + [vp, C.c_size_t, vp, C.c_size_t, ALLOC_FN, vp,
+                                                                         C.POINTER(vp), C.POINTER(C.c_int64), vp]
+    L.sgr_backward_blend.restype = C.c_int
+    L.sgr_backward_blend.argtypes = [C.POINTER(SgrFrame), C.c_int64] + [vp] * 12
+    L.sgr_backward_geom.restype = C.c_int
+    L.sgr_backward_geom.argtypes = [C.POINTER(SgrFrame)] + [vp] * 18
+    L.sgr_backward.restype = C.c_int
+    L.sgr_backward.argtypes = [C.POINTER(SgrFrame), C.c_int64] + [vp] * 27
+    L.sgr_mark_visible.restype = C.c_int
+    L.sgr_mark_visible.argtypes = [C.c_int32, vp, vp, vp, vp, vp]
+    L.sgr_visible_filter.restype = C.c_int
+    L.sgr_visible_filter.argtypes = [C.POINTER(SgrFrame)] + [vp] * 7
+    L.sgr_knn_scratch_bytes.restype = C.c_size_t
+    L.sgr_knn_scratch_bytes.argtypes = [C.c_int32]
+    L.sgr_knn_mean_dist2.restype = C.c_int
+    L.sgr_knn_mean_dist2.argtypes = [C.c_int32, vp, vp, vp, C.c_size_t, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().sgr_last_error()
+        raise SgrError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,272 @@
+// capi.cu — the extern "C" surface of libsgr.so (include/sgr.h): argument validation, state carving, launch order.
+// Host-side only; every device kernel lives in its own translation unit.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "sgr_common.cuh"
+
+namespace sgr {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+// ---- state carving: bump-pointer layout inside the caller's buffers (all sub-arrays 256-B aligned) ----
+template <typename T>
+static T *take(char *&p, size_t count) {
+	T *r = reinterpret_cast<T *>(p);
+	p += align_up(count * sizeof(T));
+	return r;
+}
+GeomView carve_geom(void *base, int P) {
+	GeomView g;
+	char *p = reinterpret_cast<char *>(base);
+	const size_t n = P > 0 ? P : 1;
+	g.rec = take<GaussRec>(p, n);
+	g.tiles_touched = take<uint32_t>(p, n);
+	g.offsets = take<uint32_t>(p, n);
+	g.scan_temp_bytes = scan_temp_bytes(P);
+	g.scan_temp = take<char>(p, g.scan_temp_bytes);
+	g.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
+	return g;
+}
+ImgView carve_img(void *base, int W, int H) {
+	ImgView v;
+	char *p = reinterpret_cast<char *>(base);
+	const size_t gx = (W + SGR_TILE - 1) / SGR_TILE, gy = (H + SGR_TILE - 1) / SGR_TILE;
+	v.ranges = take<uint2>(p, gx * gy + 1);
+	v.tile_max_contrib = take<uint32_t>(p, gx * gy + 1);
+	v.n_contrib = take<uint32_t>(p, (size_t)W * H + 1);
+	v.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
+	return v;
+}
+BinView carve_bin(void *base, int64_t R) {
+	BinView b;
+	char *p = reinterpret_cast<char *>(base);
+	const size_t n = R > 0 ? (size_t)R : 1;
+	b.keys_in = take<uint64_t>(p, n);
+	b.keys_out = take<uint64_t>(p, n);
+	b.vals_in = take<uint32_t>(p, n);
+	b.vals_out = take<uint32_t>(p, n);
+	b.sort_temp_bytes = sort_temp_bytes(R);
+	b.sort_temp = take<char>(p, b.sort_temp_bytes);
+	b.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
+	return b;
+}
+
+static int make_frame(const SgrFrame *fr, FrameDev &f) {
+	if (!fr) return fail(SGR_EINVAL, "frame is NULL");
+	if (fr->P < 0 || fr->width <= 0 || fr->height <= 0) return fail(SGR_EINVAL, "bad sizes P=%d W=%d H=%d", fr->P, fr->width, fr->height);
+	if (fr->S < 0 || fr->M < 0 || fr->D < 0 || fr->D > 3) return fail(SGR_EINVAL, "bad S=%d M=%d D=%d (SH degree must be 0..3)", fr->S, fr->M, fr->D);
+	f.P = fr->P; f.D = fr->D; f.M = fr->M; f.S = fr->S; f.W = fr->width; f.H = fr->height;
+	f.gx = (f.W + SGR_TILE - 1) / SGR_TILE; f.gy = (f.H + SGR_TILE - 1) / SGR_TILE;
+	f.tanx = fr->tan_fovx; f.tany = fr->tan_fovy; f.mod = fr->scale_modifier;
+	// focal lengths exactly as the reference derives them (rasterizer_impl.cu:225-226)
+	f.fy = f.H / (2.0f * f.tany);
+	f.fx = f.W / (2.0f * f.tanx);
+	if (fr->row_step == 0 && fr->row_begin == 0 && fr->row_end == 0) f.band = Band{0, f.gy, 1};
+	else {
+		if (fr->row_step <= 0 || fr->row_begin < 0 || fr->row_end > f.gy || fr->row_begin > fr->row_end)
+			return fail(SGR_EINVAL, "bad tile-row band [%d,%d) step %d for %d tile rows", fr->row_begin, fr->row_end, fr->row_step, f.gy);
+		f.band = Band{fr->row_begin, fr->row_end, fr->row_step};
+	}
+	f.bg = fr->bg; f.view = fr->viewmatrix; f.proj = fr->projmatrix; f.campos = fr->campos;
+	return SGR_OK;
+}
+
+static int check(cudaError_t e, const char *what, bool debug, cudaStream_t st) {
+	if (e == cudaSuccess && debug) e = cudaStreamSynchronize(st);
+	if (e == cudaSuccess && debug) e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(SGR_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+	return SGR_OK;
+}
+#define SGR_TRY(expr, what)                                             \
+	do {                                                                \
+		int rc_ = check((expr), what, debug, st);                       \
+		if (rc_ != SGR_OK) return rc_;                                  \
+	} while (0)
+
+}  // namespace sgr
+
+using namespace sgr;
+
+extern "C" {
+
+int sgr_abi_version(void) { return SGR_ABI_VERSION; }
+const char *sgr_last_error(void) { return g_err; }
+
+int sgr_state_sizes(const SgrFrame *frame, size_t *geom_bytes, size_t *img_bytes) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	if (geom_bytes) *geom_bytes = carve_geom(nullptr, f.P).total_bytes;
+	if (img_bytes) *img_bytes = carve_img(nullptr, f.W, f.H).total_bytes;
+	return SGR_OK;
+}
+
+size_t sgr_binning_bytes(int64_t R) { return carve_bin(nullptr, R).total_bytes; }
+
+int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                const float *semantics, const float *opacities, const float *scales, const float *rotations,
+                const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
+                int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
+                void *alloc_user, void **binning_state, int64_t *num_instances, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (binning_state) *binning_state = nullptr;
+	if (num_instances) *num_instances = 0;
+	if (!out_color || !out_depth || !out_alpha || (f.S > 0 && !out_semantic)) return fail(SGR_EINVAL, "output image pointer is NULL");
+	if (!f.bg || !f.view || !f.proj || !f.campos) return fail(SGR_EINVAL, "camera pointer (bg/viewmatrix/projmatrix/campos) is NULL");
+	if (f.P > 0) {
+		if (!means3D || !opacities || !radii) return fail(SGR_EINVAL, "means3D / opacities / radii is NULL");
+		if ((shs == nullptr) == (colors_precomp == nullptr)) return fail(SGR_EINVAL, "provide exactly one of shs / colors_precomp");
+		const bool sr = scales != nullptr && rotations != nullptr;
+		if (sr == (cov3D_precomp != nullptr) || ((scales != nullptr) != (rotations != nullptr)))
+			return fail(SGR_EINVAL, "provide exactly one of (scales, rotations) / cov3D_precomp");
+		if (shs && f.M <= 0) return fail(SGR_EINVAL, "shs given but M == 0");
+		if (f.S > 0 && !semantics) return fail(SGR_EINVAL, "S > 0 but semantics is NULL");
+	}
+	const GeomView g = carve_geom(geom_state, f.P);
+	const ImgView img = carve_img(img_state, f.W, f.H);
+	if (!geom_state || geom_bytes < g.total_bytes) return fail(SGR_ENOMEM, "geom_state too small: %zu < %zu", geom_bytes, g.total_bytes);
+	if (!img_state || img_bytes < img.total_bytes) return fail(SGR_ENOMEM, "img_state too small: %zu < %zu", img_bytes, img.total_bytes);
+
+	int64_t R = 0;
+	BinView b = carve_bin(nullptr, 0);
+	if (f.P > 0) {
+		SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
+		        "preprocess_fwd");
+		SGR_TRY(launch_scan(f, g, st), "scan");
+		uint32_t r32 = 0;
+		cudaError_t e = cudaMemcpyAsync(&r32, g.offsets + (f.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		if (e != cudaSuccess) return fail(SGR_ECUDA, "instance count read-back: %s", cudaGetErrorString(e));
+		R = (int64_t)r32;
+		if (R > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "instance count %lld exceeds 2^31-1", (long long)R);
+	}
+	if (R > 0) {
+		if (!alloc) return fail(SGR_EINVAL, "alloc callback is NULL");
+		const size_t need = carve_bin(nullptr, R).total_bytes;
+		void *bin = alloc(alloc_user, need);
+		if (!bin) return fail(SGR_ENOMEM, "binning allocator returned NULL for %zu bytes", need);
+		b = carve_bin(bin, R);
+		if (binning_state) *binning_state = bin;
+	}
+	if (num_instances) *num_instances = R;
+	SGR_TRY(launch_binning(f, g, radii, b, img, R, st), "binning");
+	SGR_TRY(launch_blend_fwd(f, g, b, img, semantics, out_color, out_depth, out_alpha, out_semantic, st), "blend_fwd");
+	return SGR_OK;
+}
+
+int sgr_backward_blend(const SgrFrame *frame, int64_t num_instances, const float *semantics, const void *geom_state,
+                       const void *binning_state, const void *img_state, const float *out_alpha, const float *dL_dcolor,
+                       const float *dL_ddepth, const float *dL_dalpha, const float *dL_dsemantic, float *grad2d,
+                       float *dL_dsemantics, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (f.P == 0) return SGR_OK;
+	if (f.S > SGR_MAX_SEMANTIC_BWD) return fail(SGR_EUNSUPPORTED, "backward supports at most %d semantic channels, got %d", SGR_MAX_SEMANTIC_BWD, f.S);
+	if (!geom_state || !img_state || !out_alpha || !dL_dcolor || !dL_ddepth || !dL_dalpha || !grad2d)
+		return fail(SGR_EINVAL, "NULL pointer passed to sgr_backward_blend");
+	if (f.S > 0 && (!semantics || !dL_dsemantic || !dL_dsemantics)) return fail(SGR_EINVAL, "S > 0 but a semantic pointer is NULL");
+	if (num_instances > 0 && !binning_state) return fail(SGR_EINVAL, "num_instances > 0 but binning_state is NULL");
+	const GeomView g = carve_geom(const_cast<void *>(geom_state), f.P);
+	const ImgView img = carve_img(const_cast<void *>(img_state), f.W, f.H);
+	const BinView b = carve_bin(const_cast<void *>(binning_state), num_instances);
+	SGR_TRY(launch_blend_bwd(f, g, b, img, semantics, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, dL_dsemantic, grad2d, dL_dsemantics, st),
+	        "blend_bwd");
+	return SGR_OK;
+}
+
+int sgr_backward_geom(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                      const float *scales, const float *rotations, const float *cov3D_precomp, const int32_t *radii,
+                      const void *geom_state, const float *grad2d, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh,
+                      float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                      float *dL_dcov3D, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (f.P == 0) return SGR_OK;
+	if (!means3D || !radii || !geom_state || !grad2d || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity)
+		return fail(SGR_EINVAL, "NULL pointer passed to sgr_backward_geom");
+	if (shs && !dL_dsh) return fail(SGR_EINVAL, "shs given but dL_dsh is NULL");
+	if (!cov3D_precomp && (!scales || !rotations || !dL_dscales || !dL_drotations))
+		return fail(SGR_EINVAL, "scale/rotation path needs scales, rotations, dL_dscales, dL_drotations");
+	const GeomView g = carve_geom(const_cast<void *>(geom_state), f.P);
+	SGR_TRY(launch_preprocess_bwd(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, g, grad2d, dL_dmeans3D,
+	                              dL_dmeans2D, shs ? dL_dsh : nullptr, dL_dcolors_precomp, dL_dopacity,
+	                              cov3D_precomp ? nullptr : dL_dscales, cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, st),
+	        "preprocess_bwd");
+	return SGR_OK;
+}
+
+int sgr_backward(const SgrFrame *frame, int64_t num_instances, const float *means3D, const float *shs,
+                 const float *colors_precomp, const float *semantics, const float *scales, const float *rotations,
+                 const float *cov3D_precomp, const int32_t *radii, const void *geom_state, const void *binning_state,
+                 const void *img_state, const float *out_alpha, const float *dL_dcolor, const float *dL_ddepth,
+                 const float *dL_dalpha, const float *dL_dsemantic, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh,
+                 float *dL_dcolors_precomp, float *dL_dsemantics, float *dL_dopacity, float *dL_dscales,
+                 float *dL_drotations, float *dL_dcov3D, float *grad2d_scratch, void *stream) {
+	int rc = sgr_backward_blend(frame, num_instances, semantics, geom_state, binning_state, img_state, out_alpha, dL_dcolor, dL_ddepth,
+	                            dL_dalpha, dL_dsemantic, grad2d_scratch, dL_dsemantics, stream);
+	if (rc) return rc;
+	return sgr_backward_geom(frame, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, geom_state, grad2d_scratch,
+	                         dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,
+	                         stream);
+}
+
+int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,
+                     void *stream) {
+	(void)projmatrix;  // the reference passes it too but the test only uses the view-space depth
+	if (P < 0) return fail(SGR_EINVAL, "P < 0");
+	if (P == 0) return SGR_OK;
+	if (!means3D || !viewmatrix || !present) return fail(SGR_EINVAL, "NULL pointer passed to sgr_mark_visible");
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_mark_visible(P, means3D, viewmatrix, present, st), "mark_visible");
+	return SGR_OK;
+}
+
+int sgr_visible_filter(const SgrFrame *frame, const float *means3D, const float *scales, const float *rotations,
+                       const float *cov3D_precomp, int32_t *radii, float *means2D, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (f.P == 0) return SGR_OK;
+	if (!means3D || !radii || !means2D || !f.view || !f.proj) return fail(SGR_EINVAL, "NULL pointer passed to sgr_visible_filter");
+	if (!cov3D_precomp && (!scales || !rotations)) return fail(SGR_EINVAL, "provide (scales, rotations) or cov3D_precomp");
+	SGR_TRY(launch_filter(f, means3D, scales, rotations, cov3D_precomp, radii, means2D, st), "visible_filter");
+	return SGR_OK;
+}
+
+size_t sgr_knn_scratch_bytes(int32_t P) { return knn_scratch_bytes(P); }
+
+int sgr_knn_mean_dist2(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes, void *stream) {
+	if (P < 0) return fail(SGR_EINVAL, "P < 0");
+	if (P == 0) return SGR_OK;
+	if (!points || !mean_dist2) return fail(SGR_EINVAL, "NULL pointer passed to sgr_knn_mean_dist2");
+	if (!scratch || scratch_bytes < knn_scratch_bytes(P)) return fail(SGR_ENOMEM, "knn scratch too small: %zu < %zu", scratch_bytes, knn_scratch_bytes(P));
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_knn(P, points, mean_dist2, scratch, scratch_bytes, st), "knn");
+	return SGR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// knn.cu — mean squared distance to the 3 nearest neighbours of every point (model initialisation only).
+//
+// Replaces simple-knn's distCUDA2 (KNN/simple_knn.cu:185-220 with coord2Morton :63-70, boxMinMax :78-117,
+// boxMeanDist :147-183).  Same exact answer — the squared distances are evaluated with the reference's expression
+// (d = other - self; d.x*d.x + d.y*d.y + d.z*d.z) and the Morton / box structure is only an exact accelerator —
+// but: no cudaMalloc/cudaFree and no blocking device->host copies per call (the reference has two of each,
+// :188,197,200,219): bounds stay on the device, all scratch is caller-owned, everything is stream-ordered; the
+// points are gathered once into Morton order (float4) so the brute-force inner loop streams contiguous memory
+// instead of chasing indices.
+#include <cfloat>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "sgr_common.cuh"
+
+namespace sgr {
+
+constexpr int kBox = 1024;
+
+struct KnnView {
+	uint32_t *bounds;  // 6 ordered-uint encoded floats: min xyz, max xyz
+	uint32_t *codes, *codes_sorted, *idx, *idx_sorted;
+	float4 *sorted_pts;
+	float *boxes;  // nbox x 6
+	void *sort_temp;
+	size_t sort_temp_bytes, total_bytes;
+};
+static size_t knn_sort_temp(int P) {
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, P > 0 ? P : 1);
+	return bytes;
+}
+static KnnView carve_knn(void *base, int P) {
+	KnnView v;
+	char *p = reinterpret_cast<char *>(base);
+	auto take = [&](size_t bytes) { char *r = p; p += align_up(bytes); return r; };
+	const size_t n = P > 0 ? P : 1, nbox = (n + kBox - 1) / kBox;
+	v.bounds = (uint32_t *)take(8 * sizeof(uint32_t));
+	v.codes = (uint32_t *)take(n * 4); v.codes_sorted = (uint32_t *)take(n * 4);
+	v.idx = (uint32_t *)take(n * 4); v.idx_sorted = (uint32_t *)take(n * 4);
+	v.sorted_pts = (float4 *)take(n * 16);
+	v.boxes = (float *)take(nbox * 6 * 4);
+	v.sort_temp_bytes = knn_sort_temp(P);
+	v.sort_temp = take(v.sort_temp_bytes);
+	v.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
+	return v;
+}
+size_t knn_scratch_bytes(int P) { return carve_knn(nullptr, P).total_bytes; }
+
+// order-preserving float <-> uint map so min/max can use integer atomics
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void knn_init_bounds(uint32_t *bounds) {
+	if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
+	else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+__global__ void __launch_bounds__(256) knn_bounds_kernel(int P, const float *__restrict__ pts, uint32_t *bounds) {
+	float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
+#pragma unroll
+		for (int k = 0; k < 3; k++) { const float v = pts[3 * (size_t)i + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
+		if ((threadIdx.x & 31) == 0) { atomicMin(bounds + k, f2ord(mn[k])); atomicMax(bounds + 3 + k, f2ord(mx[k])); }
+	}
+}
+__device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 10 bits -> every third bit
+	x = (x | (x << 16)) & 0x030000FFu;
+	x = (x | (x << 8)) & 0x0300F00Fu;
+	x = (x | (x << 4)) & 0x030C30C3u;
+	x = (x | (x << 2)) & 0x09249249u;
+	return x;
+}
+__global__ void __launch_bounds__(256) knn_morton_kernel(int P, const float *__restrict__ pts, const uint32_t *__restrict__ bounds,
+                                                        uint32_t *__restrict__ codes, uint32_t *__restrict__ idx) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	uint32_t q[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const float lo = ord2f(bounds[k]), hi = ord2f(bounds[3 + k]);
+		const float ext = hi - lo;
+		const float t = ext > 0.f ? (pts[3 * (size_t)i + k] - lo) / ext : 0.f;
+		q[k] = (uint32_t)fminf(fmaxf(t * 1023.f, 0.f), 1023.f);
+	}
+	codes[i] = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+	idx[i] = (uint32_t)i;
+}
+// gather into Morton order + one AABB per kBox consecutive points
+__global__ void __launch_bounds__(kBox) knn_boxes_kernel(int P, const float *__restrict__ pts, const uint32_t *__restrict__ idx_sorted,
+                                                        float4 *__restrict__ sorted_pts, float *__restrict__ boxes) {
+	__shared__ float s_mn[3][kBox / 32], s_mx[3][kBox / 32];
+	const int i = blockIdx.x * kBox + threadIdx.x;
+	float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	if (i < P) {
+		const uint32_t src = idx_sorted[i];
+		const float x = pts[3 * (size_t)src], y = pts[3 * (size_t)src + 1], z = pts[3 * (size_t)src + 2];
+		sorted_pts[i] = make_float4(x, y, z, __uint_as_float(src));
+		mn[0] = mx[0] = x; mn[1] = mx[1] = y; mn[2] = mx[2] = z;
+	}
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
+		if ((threadIdx.x & 31) == 0) { s_mn[k][threadIdx.x >> 5] = mn[k]; s_mx[k][threadIdx.x >> 5] = mx[k]; }
+	}
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		float a = FLT_MAX, b = -FLT_MAX;
+		for (int w = 0; w < kBox / 32; w++) { a = fminf(a, s_mn[threadIdx.x][w]); b = fmaxf(b, s_mx[threadIdx.x][w]); }
+		boxes[6 * (size_t)blockIdx.x + threadIdx.x] = a;
+		boxes[6 * (size_t)blockIdx.x + 3 + threadIdx.x] = b;
+	}
+}
+__device__ __forceinline__ void knn_update3(const float4 self, const float4 other, float *best) {
+	const float dx = other.x - self.x, dy = other.y - self.y, dz = other.z - self.z;
+	float dist = dx * dx + dy * dy + dz * dz;
+#pragma unroll
+	for (int j = 0; j < 3; j++)
+		if (best[j] > dist) { const float t = best[j]; best[j] = dist; dist = t; }
+}
+__global__ void __launch_bounds__(256) knn_search_kernel(int P, const float4 *__restrict__ sorted_pts, const float *__restrict__ boxes,
+                                                        float *__restrict__ out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const float4 self = sorted_pts[i];
+	float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+	for (int j = max(0, i - 3); j <= min(P - 1, i + 3); j++)
+		if (j != i) knn_update3(self, sorted_pts[j], best);
+	const float reject = best[2];  // upper bound of the true 3rd-nearest distance
+	best[0] = best[1] = best[2] = FLT_MAX;
+	const int nbox = (P + kBox - 1) / kBox;
+	for (int b = 0; b < nbox; b++) {
+		const float *bx = boxes + 6 * (size_t)b;
+		const float ex = fmaxf(0.f, fmaxf(bx[0] - self.x, self.x - bx[3]));
+		const float ey = fmaxf(0.f, fmaxf(bx[1] - self.y, self.y - bx[4]));
+		const float ez = fmaxf(0.f, fmaxf(bx[2] - self.z, self.z - bx[5]));
+		const float bd = ex * ex + ey * ey + ez * ez;
+		if (bd > reject || bd > best[2]) continue;
+		const int end = min(P, (b + 1) * kBox);
+		for (int j = b * kBox; j < end; j++)
+			if (j != i) knn_update3(self, sorted_pts[j], best);
+	}
+	out[__float_as_uint(self.w)] = (best[0] + best[1] + best[2]) / 3.0f;
+}
+
+cudaError_t launch_knn(int P, const float *points, float *out, void *scratch, size_t scratch_bytes, cudaStream_t st) {
+	(void)scratch_bytes;
+	KnnView v = carve_knn(scratch, P);
+	knn_init_bounds<<<1, 32, 0, st>>>(v.bounds);
+	const int nblk = (P + 255) / 256;
+	knn_bounds_kernel<<<min(nblk, 1184), 256, 0, st>>>(P, points, v.bounds);
+	knn_morton_kernel<<<nblk, 256, 0, st>>>(P, points, v.bounds, v.codes, v.idx);
+	size_t bytes = v.sort_temp_bytes;
+	cudaError_t e = cub::DeviceRadixSort::SortPairs(v.sort_temp, bytes, v.codes, v.codes_sorted, v.idx, v.idx_sorted, P, 0, 30, st);
+	if (e != cudaSuccess) return e;
+	const int nbox = (P + kBox - 1) / kBox;
+	knn_boxes_kernel<<<nbox, kBox, 0, st>>>(P, points, v.idx_sorted, v.sorted_pts, v.boxes);
+	knn_search_kernel<<<nblk, 256, 0, st>>>(P, v.sorted_pts, v.boxes, out);
+	return cudaGetLastError();
+}
+
+}  // namespace sgr

@@ -1,0 +1,279 @@
+// preprocess_bwd.cu — per-Gaussian chain rule: screen-space sums -> (mean3D, SH | colour, opacity, scale, rotation | cov3D).
+//
+// Replaces the reference's computeCov2DCUDA + preprocessCUDA(backward) pair (DGR/cuda_rasterizer/backward.cu:144-274,
+// 346-412, with computeColorFromSH :20-139 and computeCov3D :278-341) by ONE kernel:
+//   * reads the 12-float grad2d record produced by blend_bwd (one 48-B aligned load) instead of five separate arrays;
+//   * recomputes cov3D from scale/rotation instead of reading a stored copy;
+//   * WRITES every output element (zeros for culled Gaussians), so the caller allocates with torch.empty and the
+//     reference's 304 B/Gaussian of torch::zeros (rasterize_points.cu:166-176) disappears;
+//   * dL/dmean3D is accumulated in registers across the three contributions and stored once (the reference does
+//     one store + two read-modify-writes + one more inside the SH routine).
+// Formulas and evaluation order follow the reference so gradients agree to fp32 rounding.
+#include "sgr_common.cuh"
+
+namespace sgr {
+
+__device__ __constant__ float bC0 = 0.28209479177387814f;
+__device__ __constant__ float bC1 = 0.4886025119029199f;
+__device__ __constant__ float bC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                                        0.5462742152960396f};
+__device__ __constant__ float bC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                        -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+__device__ __forceinline__ M3 rot_colmajor(const float4 q) {
+	const float r = q.x, x = q.y, y = q.z, z = q.w;
+	M3 R;
+	R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+	R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+	R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+	return R;
+}
+
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(
+    const FrameDev f, const float *__restrict__ means3D, const float *__restrict__ shs, const float *__restrict__ colors_precomp,
+    const float *__restrict__ scales, const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
+    const int32_t *__restrict__ radii, const GaussRec *__restrict__ rec, const float *__restrict__ grad2d,
+    float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D, float *__restrict__ dL_dsh, float *__restrict__ dL_dcolors,
+    float *__restrict__ dL_dopacity, float *__restrict__ dL_dscales, float *__restrict__ dL_drot, float *__restrict__ dL_dcov3D) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= f.P) return;
+	const size_t i = (size_t)idx;
+	const int nsh = f.M * 3;
+	const bool visible = radii[idx] > 0;
+
+	const float4 g0 = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
+	const float4 g1 = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
+	const float4 g2 = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
+
+	dL_dmeans2D[3 * i] = g0.x; dL_dmeans2D[3 * i + 1] = g0.y; dL_dmeans2D[3 * i + 2] = g0.z;
+	dL_dopacity[i] = g1.z;
+	if (dL_dcolors) { dL_dcolors[3 * i] = g1.w; dL_dcolors[3 * i + 1] = g2.x; dL_dcolors[3 * i + 2] = g2.y; }
+
+	if (!visible) {
+		dL_dmeans3D[3 * i] = 0.f; dL_dmeans3D[3 * i + 1] = 0.f; dL_dmeans3D[3 * i + 2] = 0.f;
+		if (dL_dscales) { dL_dscales[3 * i] = 0.f; dL_dscales[3 * i + 1] = 0.f; dL_dscales[3 * i + 2] = 0.f; }
+		if (dL_drot) reinterpret_cast<float4 *>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (dL_dcov3D)
+			for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
+		if (dL_dsh)
+			for (int k = 0; k < nsh; k++) dL_dsh[i * nsh + k] = 0.f;
+		return;
+	}
+
+	const float *view = f.view, *proj = f.proj;
+	const float3 mean = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+
+	// ---- world covariance (recomputed) ----
+	float c6[6];
+	float3 s_mod = make_float3(0.f, 0.f, 0.f);
+	float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+	M3 R;
+	if (cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * i + k];
+	} else {
+		q = *reinterpret_cast<const float4 *>(rotations + 4 * i);
+		R = rot_colmajor(q);
+		s_mod = make_float3(f.mod * scales[3 * i], f.mod * scales[3 * i + 1], f.mod * scales[3 * i + 2]);
+		const M3 S = {{{s_mod.x, 0.f, 0.f}, {0.f, s_mod.y, 0.f}, {0.f, 0.f, s_mod.z}}};
+		const M3 Mm = m3_mul(S, R);
+		const M3 Sg = m3_mul(m3_t(Mm), Mm);
+		c6[0] = Sg.m[0][0]; c6[1] = Sg.m[0][1]; c6[2] = Sg.m[0][2]; c6[3] = Sg.m[1][1]; c6[4] = Sg.m[1][2]; c6[5] = Sg.m[2][2];
+	}
+
+	// ---- conic -> cov2D -> cov3D, and mean through the projection Jacobian (reference backward.cu:144-274) ----
+	const float3 dL_dconic = make_float3(g0.w, g1.x, g1.y);
+	float3 t = xform4x3(mean, view);
+	const float limx = 1.3f * f.tanx, limy = 1.3f * f.tany;
+	const float txtz = t.x / t.z, tytz = t.y / t.z;
+	t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+	t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+	const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+	const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
+	const float h_x = f.fx, h_y = f.fy;
+	const M3 J = {{{h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z)}, {0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z)}, {0.f, 0.f, 0.f}}};
+	const M3 W = {{{view[0], view[4], view[8]}, {view[1], view[5], view[9]}, {view[2], view[6], view[10]}}};
+	const M3 Vrk = {{{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}}};
+	const M3 Tm = m3_mul(W, J);
+	M3 cov2D = m3_mul(m3_mul(m3_t(Tm), m3_t(Vrk)), Tm);
+	const float a = cov2D.m[0][0] += 0.3f;
+	const float b = cov2D.m[0][1];
+	const float c = cov2D.m[1][1] += 0.3f;
+	const float denom = a * c - b * b;
+	float dL_da = 0, dL_db = 0, dL_dc = 0;
+	const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+	float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#define T_(c_, r_) Tm.m[c_][r_]
+	if (denom2inv != 0) {
+		dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+		dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+		dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+		dcov[0] = (T_(0, 0) * T_(0, 0) * dL_da + T_(0, 0) * T_(1, 0) * dL_db + T_(1, 0) * T_(1, 0) * dL_dc);
+		dcov[3] = (T_(0, 1) * T_(0, 1) * dL_da + T_(0, 1) * T_(1, 1) * dL_db + T_(1, 1) * T_(1, 1) * dL_dc);
+		dcov[5] = (T_(0, 2) * T_(0, 2) * dL_da + T_(0, 2) * T_(1, 2) * dL_db + T_(1, 2) * T_(1, 2) * dL_dc);
+		dcov[1] = 2 * T_(0, 0) * T_(0, 1) * dL_da + (T_(0, 0) * T_(1, 1) + T_(0, 1) * T_(1, 0)) * dL_db + 2 * T_(1, 0) * T_(1, 1) * dL_dc;
+		dcov[2] = 2 * T_(0, 0) * T_(0, 2) * dL_da + (T_(0, 0) * T_(1, 2) + T_(0, 2) * T_(1, 0)) * dL_db + 2 * T_(1, 0) * T_(1, 2) * dL_dc;
+		dcov[4] = 2 * T_(0, 2) * T_(0, 1) * dL_da + (T_(0, 1) * T_(1, 2) + T_(0, 2) * T_(1, 1)) * dL_db + 2 * T_(1, 1) * T_(1, 2) * dL_dc;
+	}
+	if (dL_dcov3D) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = dcov[k];
+	}
+#define V_(c_, r_) Vrk.m[c_][r_]
+	const float dL_dT00 = 2 * (T_(0, 0) * V_(0, 0) + T_(0, 1) * V_(0, 1) + T_(0, 2) * V_(0, 2)) * dL_da +
+	                      (T_(1, 0) * V_(0, 0) + T_(1, 1) * V_(0, 1) + T_(1, 2) * V_(0, 2)) * dL_db;
+	const float dL_dT01 = 2 * (T_(0, 0) * V_(1, 0) + T_(0, 1) * V_(1, 1) + T_(0, 2) * V_(1, 2)) * dL_da +
+	                      (T_(1, 0) * V_(1, 0) + T_(1, 1) * V_(1, 1) + T_(1, 2) * V_(1, 2)) * dL_db;
+	const float dL_dT02 = 2 * (T_(0, 0) * V_(2, 0) + T_(0, 1) * V_(2, 1) + T_(0, 2) * V_(2, 2)) * dL_da +
+	                      (T_(1, 0) * V_(2, 0) + T_(1, 1) * V_(2, 1) + T_(1, 2) * V_(2, 2)) * dL_db;
+	const float dL_dT10 = 2 * (T_(1, 0) * V_(0, 0) + T_(1, 1) * V_(0, 1) + T_(1, 2) * V_(0, 2)) * dL_dc +
+	                      (T_(0, 0) * V_(0, 0) + T_(0, 1) * V_(0, 1) + T_(0, 2) * V_(0, 2)) * dL_db;
+	const float dL_dT11 = 2 * (T_(1, 0) * V_(1, 0) + T_(1, 1) * V_(1, 1) + T_(1, 2) * V_(1, 2)) * dL_dc +
+	                      (T_(0, 0) * V_(1, 0) + T_(0, 1) * V_(1, 1) + T_(0, 2) * V_(1, 2)) * dL_db;
+	const float dL_dT12 = 2 * (T_(1, 0) * V_(2, 0) + T_(1, 1) * V_(2, 1) + T_(1, 2) * V_(2, 2)) * dL_dc +
+	                      (T_(0, 0) * V_(2, 0) + T_(0, 1) * V_(2, 1) + T_(0, 2) * V_(2, 2)) * dL_db;
+#undef V_
+#undef T_
+	const float dL_dJ00 = W.m[0][0] * dL_dT00 + W.m[0][1] * dL_dT01 + W.m[0][2] * dL_dT02;
+	const float dL_dJ02 = W.m[2][0] * dL_dT00 + W.m[2][1] * dL_dT01 + W.m[2][2] * dL_dT02;
+	const float dL_dJ11 = W.m[1][0] * dL_dT10 + W.m[1][1] * dL_dT11 + W.m[1][2] * dL_dT12;
+	const float dL_dJ12 = W.m[2][0] * dL_dT10 + W.m[2][1] * dL_dT11 + W.m[2][2] * dL_dT12;
+	const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+	const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+	const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+	const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+	// view^T (3x3 part) applied to (dtx, dty, dtz)
+	float3 dmean = make_float3(view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz, view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
+	                           view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz);
+
+	// ---- mean2D -> mean3D through the projective divide (reference backward.cu:375-389) ----
+	{
+		const float4 m_hom = xform4x4(mean, proj);
+		const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+		const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+		const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+		float3 d;
+		d.x = (proj[0] * m_w - proj[3] * mul1) * g0.x + (proj[1] * m_w - proj[3] * mul2) * g0.y;
+		d.y = (proj[4] * m_w - proj[7] * mul1) * g0.x + (proj[5] * m_w - proj[7] * mul2) * g0.y;
+		d.z = (proj[8] * m_w - proj[11] * mul1) * g0.x + (proj[9] * m_w - proj[11] * mul2) * g0.y;
+		dmean.x += d.x; dmean.y += d.y; dmean.z += d.z;
+	}
+	// ---- blended depth -> mean3D (reference backward.cu:392-403) ----
+	{
+		const float dL_ddepth = g2.z;
+		const float mul3 = view[2] * mean.x + view[6] * mean.y + view[10] * mean.z + view[14];
+		float3 d;
+		d.x = (view[2] - view[3] * mul3) * dL_ddepth;
+		d.y = (view[6] - view[7] * mul3) * dL_ddepth;
+		d.z = (view[10] - view[11] * mul3) * dL_ddepth;
+		dmean.x += d.x; dmean.y += d.y; dmean.z += d.z;
+	}
+
+	// ---- SH backward (reference backward.cu:20-139) ----
+	if (shs != nullptr) {
+		const float *sh = shs + i * nsh;
+		float *dsh = dL_dsh + i * nsh;
+		const uint32_t clamp_bits = __float_as_uint(rec[idx].q2.z);
+		const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
+		const float3 dir_orig = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
+		const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+		const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+		float dRGB[3] = {g1.w, g2.x, g2.y};
+		dRGB[0] *= (clamp_bits & 1u) ? 0 : 1;
+		dRGB[1] *= (clamp_bits & 2u) ? 0 : 1;
+		dRGB[2] *= (clamp_bits & 4u) ? 0 : 1;
+		const int deg = f.D;
+		const int ncoef = min(f.M, (deg + 1) * (deg + 1));
+		float ddir[3] = {0.f, 0.f, 0.f};
+		// coefficients beyond the active degree receive zero gradient
+		for (int k = ncoef * 3; k < nsh; k++) dsh[k] = 0.f;
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++) {
+#define SHC(k) __ldg(sh + (k) * 3 + ch)
+#define DSH(k) dsh[(k) * 3 + ch]
+			const float g = dRGB[ch];
+			float dx = 0.f, dy = 0.f, dz = 0.f;
+			DSH(0) = bC0 * g;
+			if (deg > 0 && ncoef >= 4) {
+				DSH(1) = (-bC1 * y) * g; DSH(2) = (bC1 * z) * g; DSH(3) = (-bC1 * x) * g;
+				dx = -bC1 * SHC(3); dy = -bC1 * SHC(1); dz = bC1 * SHC(2);
+				if (deg > 1 && ncoef >= 9) {
+					const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+					DSH(4) = (bC2[0] * xy) * g; DSH(5) = (bC2[1] * yz) * g; DSH(6) = (bC2[2] * (2.f * zz - xx - yy)) * g;
+					DSH(7) = (bC2[3] * xz) * g; DSH(8) = (bC2[4] * (xx - yy)) * g;
+					dx += bC2[0] * y * SHC(4) + bC2[2] * 2.f * -x * SHC(6) + bC2[3] * z * SHC(7) + bC2[4] * 2.f * x * SHC(8);
+					dy += bC2[0] * x * SHC(4) + bC2[1] * z * SHC(5) + bC2[2] * 2.f * -y * SHC(6) + bC2[4] * 2.f * -y * SHC(8);
+					dz += bC2[1] * y * SHC(5) + bC2[2] * 2.f * 2.f * z * SHC(6) + bC2[3] * x * SHC(7);
+					if (deg > 2 && ncoef >= 16) {
+						DSH(9) = (bC3[0] * y * (3.f * xx - yy)) * g; DSH(10) = (bC3[1] * xy * z) * g;
+						DSH(11) = (bC3[2] * y * (4.f * zz - xx - yy)) * g; DSH(12) = (bC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g;
+						DSH(13) = (bC3[4] * x * (4.f * zz - xx - yy)) * g; DSH(14) = (bC3[5] * z * (xx - yy)) * g;
+						DSH(15) = (bC3[6] * x * (xx - 3.f * yy)) * g;
+						dx += (bC3[0] * SHC(9) * 3.f * 2.f * xy + bC3[1] * SHC(10) * yz + bC3[2] * SHC(11) * -2.f * xy +
+						       bC3[3] * SHC(12) * -3.f * 2.f * xz + bC3[4] * SHC(13) * (-3.f * xx + 4.f * zz - yy) +
+						       bC3[5] * SHC(14) * 2.f * xz + bC3[6] * SHC(15) * 3.f * (xx - yy));
+						dy += (bC3[0] * SHC(9) * 3.f * (xx - yy) + bC3[1] * SHC(10) * xz + bC3[2] * SHC(11) * (-3.f * yy + 4.f * zz - xx) +
+						       bC3[3] * SHC(12) * -3.f * 2.f * yz + bC3[4] * SHC(13) * -2.f * xy + bC3[5] * SHC(14) * -2.f * yz +
+						       bC3[6] * SHC(15) * -3.f * 2.f * xy);
+						dz += (bC3[1] * SHC(10) * xy + bC3[2] * SHC(11) * 4.f * 2.f * yz + bC3[3] * SHC(12) * 3.f * (2.f * zz - xx - yy) +
+						       bC3[4] * SHC(13) * 4.f * 2.f * xz + bC3[5] * SHC(14) * (xx - yy));
+					}
+				}
+			}
+#undef SHC
+#undef DSH
+			ddir[0] += dx * g; ddir[1] += dy * g; ddir[2] += dz * g;
+		}
+		// through the normalisation of the view direction (reference dnormvdv, auxiliary.h:107-117)
+		const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
+		const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+		dmean.x += ((+sum2 - dir_orig.x * dir_orig.x) * ddir[0] - dir_orig.y * dir_orig.x * ddir[1] - dir_orig.z * dir_orig.x * ddir[2]) * invsum32;
+		dmean.y += (-dir_orig.x * dir_orig.y * ddir[0] + (sum2 - dir_orig.y * dir_orig.y) * ddir[1] - dir_orig.z * dir_orig.y * ddir[2]) * invsum32;
+		dmean.z += (-dir_orig.x * dir_orig.z * ddir[0] - dir_orig.y * dir_orig.z * ddir[1] + (sum2 - dir_orig.z * dir_orig.z) * ddir[2]) * invsum32;
+	}
+	dL_dmeans3D[3 * i] = dmean.x; dL_dmeans3D[3 * i + 1] = dmean.y; dL_dmeans3D[3 * i + 2] = dmean.z;
+
+	// ---- cov3D -> scale, raw quaternion (reference backward.cu:278-341; no normalisation Jacobian, scale_modifier quirk kept) ----
+	if (cov3D_precomp == nullptr) {
+		const float r = q.x, x = q.y, y = q.z, z = q.w;
+		const M3 S = {{{s_mod.x, 0.f, 0.f}, {0.f, s_mod.y, 0.f}, {0.f, 0.f, s_mod.z}}};
+		const M3 Mm = m3_mul(S, R);
+		const M3 dSig = {{{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}}};
+		M3 M2;
+#pragma unroll
+		for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+			for (int rr = 0; rr < 3; rr++) M2.m[cc][rr] = Mm.m[cc][rr] * 2.0f;
+		const M3 dL_dM = m3_mul(M2, dSig);
+		const M3 Rt = m3_t(R);
+		M3 dMt = m3_t(dL_dM);
+		dL_dscales[3 * i] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+		dL_dscales[3 * i + 1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+		dL_dscales[3 * i + 2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+		for (int k = 0; k < 3; k++) { dMt.m[0][k] *= s_mod.x; dMt.m[1][k] *= s_mod.y; dMt.m[2][k] *= s_mod.z; }
+#define D_(c_, r_) dMt.m[c_][r_]
+		float4 dq;
+		dq.x = 2 * z * (D_(0, 1) - D_(1, 0)) + 2 * y * (D_(2, 0) - D_(0, 2)) + 2 * x * (D_(1, 2) - D_(2, 1));
+		dq.y = 2 * y * (D_(1, 0) + D_(0, 1)) + 2 * z * (D_(2, 0) + D_(0, 2)) + 2 * r * (D_(1, 2) - D_(2, 1)) - 4 * x * (D_(2, 2) + D_(1, 1));
+		dq.z = 2 * x * (D_(1, 0) + D_(0, 1)) + 2 * r * (D_(2, 0) - D_(0, 2)) + 2 * z * (D_(1, 2) + D_(2, 1)) - 4 * y * (D_(2, 2) + D_(0, 0));
+		dq.w = 2 * r * (D_(0, 1) - D_(1, 0)) + 2 * x * (D_(2, 0) + D_(0, 2)) + 2 * y * (D_(1, 2) + D_(2, 1)) - 4 * z * (D_(1, 1) + D_(0, 0));
+#undef D_
+		reinterpret_cast<float4 *>(dL_drot)[i] = dq;
+	}
+}
+
+cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
+                                  const float *scales, const float *rotations, const float *cov3D_precomp,
+                                  const int32_t *radii, GeomView g, const float *grad2d, float *dL_dmeans3D,
+                                  float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity,
+                                  float *dL_dscales, float *dL_drot, float *dL_dcov3D, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	(void)colors_precomp;
+	preprocess_bwd_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii,
+	                                                         g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity,
+	                                                         dL_dscales, dL_drot, dL_dcov3D);
+	return cudaGetLastError();
+}
+
+}  // namespace sgr

@@ -1,0 +1,237 @@
+// preprocess_fwd.cu — per-Gaussian forward stage: project, EWA covariance, conic, radius, SH -> RGB, exact tile count.
+//
+// One thread per Gaussian (HBM-bound; algorithmic bytes per Gaussian in DESIGN.md §4).  Replaces the reference's
+// preprocessCUDA / filter_preprocessCUDA / checkFrustum (DGR/cuda_rasterizer/forward.cu:155-334,
+// rasterizer_impl.cu:54-66).  The arithmetic keeps the reference's expression shapes so that depth, conic, radius and
+// RGB are bit-equal (the tile sort key is the raw depth bits; a 1-ulp difference could swap two splats).
+//
+// What is new relative to the reference: (1) the packed 48-B GaussRec output, (2) cov3D is not stored (backward
+// recomputes it), (3) tiles_touched counts only the tiles of the 3-sigma rectangle that can actually receive a
+// contribution (exact opacity-aware cull, sgr_common.cuh) and that lie in this process's tile-row band,
+// (4) large rectangles are counted warp-cooperatively instead of by one thread.
+#include "sgr_common.cuh"
+#include "tile_visit.cuh"
+
+namespace sgr {
+
+__device__ __constant__ float kC0 = 0.28209479177387814f;
+__device__ __constant__ float kC1 = 0.4886025119029199f;
+__device__ __constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                                        0.5462742152960396f};
+__device__ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                        -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+// world-space covariance from (modifier * scale, raw quaternion) — the quaternion is deliberately not normalised
+// (reference forward.cu:127).  Upper triangle: xx xy xz yy yz zz.
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 s, const float mod, const float4 q, float *c6) {
+	const float r = q.x, x = q.y, y = q.z, z = q.w;
+	M3 R;  // column-major; column 0 = first row of the usual rotation matrix
+	R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+	R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+	R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+	M3 S = {{{mod * s.x, 0.f, 0.f}, {0.f, mod * s.y, 0.f}, {0.f, 0.f, mod * s.z}}};
+	const M3 Mm = m3_mul(S, R);
+	const M3 Sg = m3_mul(m3_t(Mm), Mm);
+	c6[0] = Sg.m[0][0]; c6[1] = Sg.m[0][1]; c6[2] = Sg.m[0][2]; c6[3] = Sg.m[1][1]; c6[4] = Sg.m[1][2]; c6[5] = Sg.m[2][2];
+}
+
+// EWA screen-space covariance (+0.3 low-pass), reference forward.cu:74-113.
+__device__ __forceinline__ float3 cov2d_ewa(const float3 mean, float fx, float fy, float tanx, float tany, const float *c6,
+                                            const float *__restrict__ view) {
+	float3 t = xform4x3(mean, view);
+	const float limx = 1.3f * tanx, limy = 1.3f * tany;
+	const float txtz = t.x / t.z, tytz = t.y / t.z;
+	t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+	t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+	const M3 J = {{{fx / t.z, 0.0f, -(fx * t.x) / (t.z * t.z)}, {0.0f, fy / t.z, -(fy * t.y) / (t.z * t.z)}, {0.f, 0.f, 0.f}}};
+	const M3 Wm = {{{view[0], view[4], view[8]}, {view[1], view[5], view[9]}, {view[2], view[6], view[10]}}};
+	const M3 T = m3_mul(Wm, J);
+	const M3 V = {{{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}}};
+	M3 cov = m3_mul(m3_mul(m3_t(T), m3_t(V)), T);
+	cov.m[0][0] += 0.3f;
+	cov.m[1][1] += 0.3f;
+	return make_float3(cov.m[0][0], cov.m[0][1], cov.m[1][1]);
+}
+
+struct Projected {
+	bool ok;
+	float depth, px, py;
+	float3 conic;
+	int radius;
+	int x0, y0, x1, y1;
+};
+
+// Shared front half of preprocess / visible_filter: cull, project, conic, radius, tile rectangle.
+__device__ __forceinline__ Projected project_gaussian(const FrameDev &f, int idx, const float3 p, const float *__restrict__ scales,
+                                                      const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp) {
+	Projected o;
+	o.ok = false;
+	o.radius = 0;
+	const float4 p_hom = xform4x4(p, f.proj);
+	const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+	const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+	const float3 p_view = xform4x3(p, f.view);
+	if (p_view.z <= 0.2f) return o;  // near cull only (reference auxiliary.h:154)
+	float c6[6];
+	if (cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * (size_t)idx + k];
+	} else {
+		const float3 s = make_float3(scales[3 * (size_t)idx], scales[3 * (size_t)idx + 1], scales[3 * (size_t)idx + 2]);
+		const float4 q = *reinterpret_cast<const float4 *>(rotations + 4 * (size_t)idx);
+		cov3d_from_scale_rot(s, f.mod, q, c6);
+	}
+	const float3 cov = cov2d_ewa(p, f.fx, f.fy, f.tanx, f.tany, c6, f.view);
+	const float det = (cov.x * cov.z - cov.y * cov.y);
+	if (det == 0.0f) return o;
+	const float det_inv = 1.f / det;
+	o.conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+	const float mid = 0.5f * (cov.x + cov.z);
+	const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+	const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+	const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+	o.px = ndc2pix(p_proj.x, f.W);
+	o.py = ndc2pix(p_proj.y, f.H);
+	o.radius = (int)my_radius;
+	tile_rect(o.px, o.py, o.radius, f.gx, f.gy, o.x0, o.y0, o.x1, o.y1);
+	if ((o.x1 - o.x0) * (o.y1 - o.y0) == 0) {
+		o.radius = 0;
+		return o;
+	}
+	o.depth = p_view.z;
+	o.ok = true;
+	return o;
+}
+
+// SH (degree <= 3) -> RGB with +0.5 and clamp-at-zero flags (reference forward.cu:20-71).  sh points at this
+// Gaussian's [M,3] block.
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float3 campos, const float *__restrict__ sh, int M,
+                                            uint32_t &clamp_bits) {
+	float3 d = make_float3(p.x - campos.x, p.y - campos.y, p.z - campos.z);
+	const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+	const float x = d.x / len, y = d.y / len, z = d.z / len;
+	float c[48];
+	const int n = min(M, (deg + 1) * (deg + 1)) * 3;
+	if (((M * 3) & 3) == 0) {
+		const float4 *s4 = reinterpret_cast<const float4 *>(sh);
+#pragma unroll
+		for (int k = 0; k < 12; k++)
+			if (4 * k < n) {
+				const float4 v = __ldg(s4 + k);
+				c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+			}
+	} else {
+#pragma unroll
+		for (int k = 0; k < 48; k++)
+			if (k < n) c[k] = __ldg(sh + k);
+	}
+	float res[3];
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) {
+#define SHC(k) c[(k) * 3 + ch]
+		float r = kC0 * SHC(0);
+		if (deg > 0) {
+			r = r - kC1 * y * SHC(1) + kC1 * z * SHC(2) - kC1 * x * SHC(3);
+			if (deg > 1) {
+				const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+				r = r + kC2[0] * xy * SHC(4) + kC2[1] * yz * SHC(5) + kC2[2] * (2.0f * zz - xx - yy) * SHC(6) +
+				    kC2[3] * xz * SHC(7) + kC2[4] * (xx - yy) * SHC(8);
+				if (deg > 2) {
+					r = r + kC3[0] * y * (3.0f * xx - yy) * SHC(9) + kC3[1] * xy * z * SHC(10) +
+					    kC3[2] * y * (4.0f * zz - xx - yy) * SHC(11) + kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHC(12) +
+					    kC3[4] * x * (4.0f * zz - xx - yy) * SHC(13) + kC3[5] * z * (xx - yy) * SHC(14) +
+					    kC3[6] * x * (xx - 3.0f * yy) * SHC(15);
+				}
+			}
+		}
+#undef SHC
+		r += 0.5f;
+		res[ch] = r;
+	}
+	clamp_bits = (res[0] < 0 ? 1u : 0u) | (res[1] < 0 ? 2u : 0u) | (res[2] < 0 ? 4u : 0u);
+	return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, const float *__restrict__ means3D,
+                                                             const float *__restrict__ shs, const float *__restrict__ colors_precomp,
+                                                             const float *__restrict__ opacities, const float *__restrict__ scales,
+                                                             const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
+                                                             int32_t *__restrict__ radii, GaussRec *__restrict__ rec,
+                                                             uint32_t *__restrict__ tiles_touched) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in_range = idx < f.P;
+	Projected pr;
+	pr.ok = false;
+	pr.radius = 0;
+	CullParams cp = {};
+	if (in_range) {
+		const float3 p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
+		pr = project_gaussian(f, idx, p, scales, rotations, cov3D_precomp);
+		if (pr.ok) {
+			float3 rgb;
+			uint32_t clamp_bits = 0;
+			if (colors_precomp == nullptr) {
+				const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
+				rgb = sh_to_rgb(f.D, p, campos, shs + (size_t)idx * f.M * 3, f.M, clamp_bits);
+			} else {
+				rgb = make_float3(colors_precomp[3 * (size_t)idx], colors_precomp[3 * (size_t)idx + 1], colors_precomp[3 * (size_t)idx + 2]);
+			}
+			const float opacity = opacities[idx];
+			GaussRec r;
+			r.q0 = make_float4(pr.px, pr.py, pr.conic.x, pr.conic.y);
+			r.q1 = make_float4(pr.conic.z, opacity, pr.depth, rgb.x);
+			r.q2 = make_float4(rgb.y, rgb.z, __uint_as_float(clamp_bits), 0.f);
+			rec[idx] = r;
+			cp = make_cull(pr.px, pr.py, pr.conic.x, pr.conic.y, pr.conic.z, opacity);
+		}
+		radii[idx] = pr.radius;
+	}
+	uint32_t count = 0;
+	visit_tiles<false>(pr.ok, pr.x0, pr.y0, pr.x1, pr.y1, cp, f.band, f.gx, 0u, 0u, 0u, nullptr, nullptr, count);
+	if (in_range) tiles_touched[idx] = count;
+}
+
+// radii + means2D only (reference filter_preprocessCUDA, forward.cu:259-334)
+__global__ void __launch_bounds__(256) filter_kernel(const FrameDev f, const float *__restrict__ means3D, const float *__restrict__ scales,
+                                                     const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
+                                                     int32_t *__restrict__ radii, float *__restrict__ means2D) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= f.P) return;
+	const float3 p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
+	const Projected pr = project_gaussian(f, idx, p, scales, rotations, cov3D_precomp);
+	radii[idx] = pr.radius;
+	means2D[2 * (size_t)idx] = pr.ok ? pr.px : 0.f;
+	means2D[2 * (size_t)idx + 1] = pr.ok ? pr.py : 0.f;
+}
+
+// present = z_view > 0.2 (reference checkFrustum, rasterizer_impl.cu:54-66)
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ view,
+                                                           uint8_t *__restrict__ present) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	const float3 p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
+	const float3 pv = xform4x3(p, view);
+	present[idx] = pv.z > 0.2f ? 1 : 0;
+}
+
+cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
+                                  const float *opacities, const float *scales, const float *rotations,
+                                  const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	preprocess_fwd_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
+	                                                         cov3D_precomp, radii, g.rec, g.tiles_touched);
+	return cudaGetLastError();
+}
+cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,
+                          const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	filter_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, scales, rotations, cov3D_precomp, radii, means2D);
+	return cudaGetLastError();
+}
+cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st) {
+	if (P == 0) return cudaSuccess;
+	mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, view, present);
+	return cudaGetLastError();
+}
+
+}  // namespace sgr
