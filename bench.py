@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — rasterizer fwd+bwd frames/s on the BASELINE.json workload, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl sgr|reference] [--workload C|B|E|A]
+
+A "step" = one forward + backward pass of the rasterizer over one synthetic frame (config C of BASELINE.md by default:
+1.5M background + 8x50k vehicle Gaussians, 1920x1280, SH degree 3).  Prints ONE JSON line (rank 0).
+
+  value      : frames/s with the Gaussian parameters already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e        : same metric through the public API starting from PINNED HOST buffers: every step copies that step's inputs
+               host->device (double-buffered on a copy stream) and reads the scalar loss back device->host
+  roofline   : dominant kernel (blend_bwd), algorithmic bytes / CUDA-event time / measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline: the CPU oracle port (oracle/sgr_oracle.c, OpenMP) on a bounded sample of the same frame
+  --impl reference : the UNMODIFIED reference CUDA rasterizer built from /root/reference sources into oracle/_ref
+               (stock code path through its own Python API), same workload/metric/timing; the reference has no CPU
+               implementation of this path, so the CPU port is reported beside it in cpu_baseline.  If oracle/_ref is
+               absent the arm times the CPU oracle port instead.
+N > 1: strong scaling — the SAME frame is tile-row sharded across ranks (street_gaussians_b200.sharded), one NCCL
+all-reduce of the per-Gaussian screen-space gradient sums per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from street_gaussians_b200 import synthetic  # noqa: E402
+
+PARAM_KEYS = ("means3D", "shs", "opacities", "scales", "rotations")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="sgr", choices=["sgr", "reference"])
+    ap.add_argument("--workload", default="C", choices=list(synthetic.CONFIGS.keys()))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-stride", type=int, default=0, help="CPU baseline uses every k-th Gaussian (0 = auto)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_settings(mod, cam, dev):
+    return mod.GaussianRasterizationSettings(
+        image_height=cam["image_height"], image_width=cam["image_width"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+        bg=cam["bg"].to(dev), scale_modifier=cam["scale_modifier"], viewmatrix=cam["viewmatrix"].to(dev),
+        projmatrix=cam["projmatrix"].to(dev), sh_degree=cam["sh_degree"], campos=cam["campos"].to(dev), prefiltered=False,
+        debug=False)
+
+
+def cpu_baseline(scene, stride: int, budget_pairs: float = 6e8):
+    """CPU oracle port on every `stride`-th Gaussian of the same frame at full resolution; linear extrapolation in P."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import oracle as O
+    P = scene["means3D"].shape[0]
+    H, W = scene["cam"]["image_height"], scene["cam"]["image_width"]
+    if stride <= 0:  # auto: aim for a few 1e8 (pixel, splat) evaluations ~ 10-30 s on 8 cores
+        stride = max(1, int(P * 12 * 256 / budget_pairs))
+    sub = {k: (v[::stride].contiguous() if (torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == P) else v) for k, v in scene.items()}
+    cam = scene["cam"]
+    c = O.Camera(H, W, cam["tanfovx"], cam["tanfovy"], cam["bg"].numpy(), cam["scale_modifier"], cam["viewmatrix"].numpy(),
+                 cam["projmatrix"].numpy(), cam["sh_degree"], cam["campos"].numpy())
+    cores = O.num_threads()
+    t0 = time.perf_counter()
+    fw = O.Forward(c, sub["means3D"], sub["opacities"], shs=sub["shs"], scales=sub["scales"], rotations=sub["rotations"])
+    fw.backward(scene["grad_color"], scene["grad_depth"], scene["grad_alpha"])
+    dt = time.perf_counter() - t0
+    n_sub = sub["means3D"].shape[0]
+    fps_full = 1.0 / (dt * (P / n_sub))
+    info = dict(value=fps_full, unit="frames/s", cores=cores, kind="port",
+                sample=f"every {stride}th Gaussian ({n_sub} of {P}) of the same frame at full {W}x{H}, fwd+bwd, {dt:.2f} s measured, "
+                       f"extrapolated x{P / n_sub:.1f} in Gaussian count; R_sample={fw.num_rendered}, pairs={fw.pairs_evaluated}")
+    fw.close()
+    return info
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        if world > 1:  # the reference is single-GPU: rank 0 alone runs it
+            pass
+        return 0
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device", "impl": args.impl}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    use_dist = world > 1 and args.impl == "sgr"
+    if use_dist:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "ref_dgr", "_C.so")
+    ref_cuda = args.impl == "reference" and os.path.exists(ref_so)
+    cpu_only_reference = args.impl == "reference" and not ref_cuda
+
+    scene = synthetic.make_config(args.workload, seed=0)
+    cam = scene["cam"]
+    P = scene["means3D"].shape[0]
+    H, W = cam["image_height"], cam["image_width"]
+    wl_desc = {"C": "config C: 1.5M background + 8x50k vehicle Gaussians composed, 1920x1280, SH deg 3, fwd+bwd",
+               "B": "config B: 500k Gaussians static scene, 1920x1280, SH deg 3, fwd+bwd",
+               "E": "config E: 8M Gaussians, 3840x2160, SH deg 3", "A": "config A: smoke-script replay 10k, 256x256",
+               "A_native": "config A native: smoke-script replay 10k, 1242x375"}[args.workload]
+
+    if cpu_only_reference:
+        cb = cpu_baseline(scene, args.cpu_sample_stride)
+        line = dict(metric="rasterizer_fwd_bwd_fps", value=cb["value"], unit="frames/s", n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=1000.0 / cb["value"], higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f32", data="synthetic", impl="reference", config=dict(workload=wl_desc, P=P, width=W, height=H),
+                    cpu_baseline=cb, e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, note="oracle/_ref (reference CUDA build) absent: CPU oracle port timed instead")
+        print(json.dumps(line))
+        return 0
+
+    if ref_cuda:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        import ref_dgr as mod
+        rast = mod.GaussianRasterizer(make_settings(mod, cam, dev))
+    else:
+        import street_gaussians_b200 as mod
+        from street_gaussians_b200.sharded import ShardedGaussianRasterizer
+        rast = ShardedGaussianRasterizer(make_settings(mod, cam, dev))
+
+    params = {k: scene[k].to(dev).requires_grad_(True) for k in PARAM_KEYS}
+    means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+    gc, gd, ga = (scene[k].to(dev) for k in ("grad_color", "grad_depth", "grad_alpha"))
+    if use_dist:  # band-local loss: upstream grads are only defined on this rank's rows
+        from street_gaussians_b200.sharded import band_of_rows
+        m = band_of_rows(H, rank, world).to(dev).view(1, H, 1).float()
+        gc, gd, ga = gc * m, gd * m, ga * m
+
+    def step(p=params):
+        for v in p.values():
+            v.grad = None
+        means2D.grad = None
+        color, radii, depth, alpha, sem = rast(means3D=p["means3D"], means2D=means2D, opacities=p["opacities"], shs=p["shs"],
+                                               scales=p["scales"], rotations=p["rotations"])
+        torch.autograd.backward([color, depth, alpha], [gc, gd, ga])
+        return color, radii
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        color, radii = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if use_dist:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    visible = int((radii > 0).sum().item())
+
+    # ---- per-stage device times (CUDA events around the staged C-ABI calls) + roofline of the dominant kernel ----
+    roofline, stages, n_inst = None, {}, None
+    if not ref_cuda:
+        from street_gaussians_b200 import rasterizer as R
+        st_obj = make_settings(mod, cam, dev)
+        band = rast.band
+        with torch.no_grad():
+            def ev():
+                return torch.cuda.Event(enable_timing=True)
+            acc = {"forward": [], "blend_bwd": [], "preprocess_bwd": []}
+            for it in range(3 + 5):
+                a, b, c, d = ev(), ev(), ev(), ev()
+                a.record()
+                col, rad, dep, alp, sem, fst, tens = R._forward_impl(params["means3D"], params["shs"], None, None, params["opacities"],
+                                                                      params["scales"], params["rotations"], None, st_obj, band)
+                b.record()
+                g2d, gsem = R._backward_blend_impl(st_obj, band, fst, tens, alp, gc, gd, ga, None)
+                c.record()
+                R._backward_geom_impl(st_obj, band, fst, tens, rad, g2d)
+                d.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    acc["forward"].append(a.elapsed_time(b)); acc["blend_bwd"].append(b.elapsed_time(c)); acc["preprocess_bwd"].append(c.elapsed_time(d))
+            stages = {k: float(np.median(v)) for k, v in acc.items()}
+            n_inst = int(fst.num_instances)
+        npx = W * H
+        # blend_bwd = R*44 + Npx*28 + V*44 bytes (R = this library's instance count, this rank's band)
+        rows_frac = 1.0 / world if use_dist else 1.0
+        alg_bytes = n_inst * 44 + npx * rows_frac * 28 + visible * 44
+        peak, peak_src = measured_peaks()
+        achieved = alg_bytes / (stages["blend_bwd"] * 1e-3) / 1e9
+        roofline = dict(bound="hbm", kernel="blend_bwd_kernel<0>", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                        traffic=None, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
+                        note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the "
+                             "contract asks; kernel_ms includes two cudaMemsetAsync of the accumulators")
+
+    # ---- end to end from pinned host memory ----
+    host = {k: scene[k].pin_memory() for k in PARAM_KEYS}
+    h2d_bytes = sum(v.numel() * 4 for v in host.values())
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i])
+            for k in PARAM_KEYS:
+                bufs[i][k].copy_(host[k], non_blocking=True)
+            ready[i].record(copy_stream)
+
+    def e2e_step(i):
+        torch.cuda.current_stream().wait_event(ready[i])
+        p = {k: bufs[i][k].detach().requires_grad_(True) for k in PARAM_KEYS}
+        color, radii, depth, alpha, sem = rast(means3D=p["means3D"], means2D=means2D, opacities=p["opacities"], shs=p["shs"],
+                                               scales=p["scales"], rotations=p["rotations"])
+        loss = (color * gc).sum() + (depth * gd).sum() + (alpha * ga).sum()
+        loss.backward()
+        consumed[i].record()
+        loss_host.copy_(loss.detach().view(1), non_blocking=True)
+
+    for ev_ in consumed:
+        ev_.record()
+    n_e2e = max(3, min(args.steps, 10))
+    upload(0)
+    for i in range(3):  # warm-up
+        upload((i + 1) % 2)
+        e2e_step(i % 2)
+    barrier()
+    upload(0)
+    e0.record()
+    for i in range(n_e2e):
+        upload((i + 1) % 2)
+        e2e_step(i % 2)
+    e1.record()
+    barrier()
+    _ = float(loss_host.item())
+    e2e_ms = e0.elapsed_time(e1) / n_e2e
+    if use_dist:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        cb = None if args.no_cpu_baseline else cpu_baseline(scene, args.cpu_sample_stride)
+        fps = 1000.0 / ms_step
+        line = dict(metric="rasterizer_fwd_bwd_fps", value=fps, unit="frames/s", n_gpus=world if use_dist else 1, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f32", data="synthetic (seeded; street_gaussians_b200/synthetic.py)",
+                    config=dict(workload=wl_desc, P=P, visible=visible, width=W, height=H, sh_degree=cam["sh_degree"],
+                                l2="inputs (%.0f MB of Gaussian parameters) exceed the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6),
+                                parallelism=("tile-row sharded x%d (cyclic rows), 1 NCCL all-reduce of grad2d[P,12]/step" % world) if use_dist else "single GPU",
+                                num_instances=n_inst, gaussians_pixels_per_s=P * W * H * fps, stage_ms=stages),
+                    e2e=dict(value=1000.0 / e2e_ms, unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
+                             note="pinned host -> device copy of all 59 floats/Gaussian every step, double-buffered on a copy stream; scalar loss read back"),
+                    gpu_launches=(16 * args.steps) if not ref_cuda else 0, clocks=clocks)
+        if roofline:
+            line["roofline"] = roofline
+        if cb:
+            line["cpu_baseline"] = cb
+        if ref_cuda:
+            line["impl"] = "reference"
+            line["config"]["reference"] = "unmodified DGR sources compiled for sm_100 into oracle/_ref (stock CUDA rasterizer, on the GPU)"
+            line["gpu_launches"] = 0
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -79,7 +79,7 @@ def _field(gen, n, tanx, tany, zmin=2.0, zmax=80.0, near_frac=0.02, scale_med=0.
 
 def make_scene(P: int, width: int, height: int, sh_degree: int = 3, seed: int = 0, n_vehicles: int = 0,
                per_vehicle: int = 0, semantics: int = 0, pose: bool = False, fovx_deg: float = 50.0,
-               bg=(0.0, 0.0, 0.0), scale_med: float = 0.05) -> Dict:
+               bg=(0.0, 0.0, 0.0), scale_med: float = 0.007) -> Dict:
     """P background Gaussians (+ n_vehicles x per_vehicle posed 'vehicle' clusters, composed the way
     lib/models/street_gaussian_model.py:335-363 does: x_world = R_obj x_local + t_obj, q_world = q_obj * q_local)."""
     gen = torch.Generator().manual_seed(seed)
