@@ -31,9 +31,13 @@ GeomView carve_geom(void *base, int P) {
 	const size_t n = P > 0 ? P : 1;
 	g.rec = take<GaussRec>(p, n);
 	g.tiles_touched = take<uint32_t>(p, n);
+	g.depth_key = take<uint32_t>(p, n);
+	g.iota = take<uint32_t>(p, n);
+	g.depth_sorted = take<uint32_t>(p, n);
+	g.perm = take<uint32_t>(p, n);
 	g.offsets = take<uint32_t>(p, n);
-	g.scan_temp_bytes = scan_temp_bytes(P);
-	g.scan_temp = take<char>(p, g.scan_temp_bytes);
+	g.temp_bytes = geom_temp_bytes(P);
+	g.temp = take<char>(p, g.temp_bytes);
 	g.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
 	return g;
 }
@@ -51,8 +55,8 @@ BinView carve_bin(void *base, int64_t R) {
 	BinView b;
 	char *p = reinterpret_cast<char *>(base);
 	const size_t n = R > 0 ? (size_t)R : 1;
-	b.keys_in = take<uint64_t>(p, n);
-	b.keys_out = take<uint64_t>(p, n);
+	b.keys_in = take<uint32_t>(p, n);
+	b.keys_out = take<uint32_t>(p, n);
 	b.vals_in = take<uint32_t>(p, n);
 	b.vals_out = take<uint32_t>(p, n);
 	b.sort_temp_bytes = sort_temp_bytes(R);
@@ -146,7 +150,7 @@ int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, c
 	if (f.P > 0) {
 		SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
 		        "preprocess_fwd");
-		SGR_TRY(launch_scan(f, g, st), "scan");
+		SGR_TRY(launch_depth_order(f, g, st), "depth_order");
 		uint32_t r32 = 0;
 		cudaError_t e = cudaMemcpyAsync(&r32, g.offsets + (f.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(st);

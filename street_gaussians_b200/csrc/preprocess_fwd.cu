@@ -7,8 +7,9 @@
 //
 // What is new relative to the reference: (1) the packed 48-B GaussRec output, (2) cov3D is not stored (backward
 // recomputes it), (3) tiles_touched counts only the tiles of the 3-sigma rectangle that can actually receive a
-// contribution (exact opacity-aware cull, sgr_common.cuh) and that lie in this process's tile-row band,
-// (4) large rectangles are counted warp-cooperatively instead of by one thread.
+// contribution (exact opacity-aware row-span cull, tile_visit.cuh) and that lie in this process's tile-row band,
+// (4) large rectangles are counted warp-cooperatively instead of by one thread, (5) a 32-bit depth key per Gaussian
+// feeds the depth pre-sort of binning.cu.
 #include "sgr_common.cuh"
 #include "tile_visit.cuh"
 
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
                                                              const float *__restrict__ opacities, const float *__restrict__ scales,
                                                              const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                                                              int32_t *__restrict__ radii, GaussRec *__restrict__ rec,
-                                                             uint32_t *__restrict__ tiles_touched) {
+                                                             uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ depth_key,
+                                                             uint32_t *__restrict__ iota) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = idx < f.P;
 	Projected pr;
@@ -187,8 +189,13 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		radii[idx] = pr.radius;
 	}
 	uint32_t count = 0;
-	visit_tiles<false>(pr.ok, pr.x0, pr.y0, pr.x1, pr.y1, cp, f.band, f.gx, 0u, 0u, 0u, nullptr, nullptr, count);
-	if (in_range) tiles_touched[idx] = count;
+	visit_tiles<false>(pr.ok, pr.x0, pr.y0, pr.x1, pr.y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
+	if (in_range) {
+		tiles_touched[idx] = count;
+		// sort key of the depth pre-sort: Gaussians that emit nothing go to the very end
+		depth_key[idx] = count > 0 ? __float_as_uint(pr.depth) : 0xffffffffu;
+		iota[idx] = (uint32_t)idx;
+	}
 }
 
 // radii + means2D only (reference filter_preprocessCUDA, forward.cu:259-334)
@@ -219,7 +226,7 @@ cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
 	preprocess_fwd_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
-	                                                         cov3D_precomp, radii, g.rec, g.tiles_touched);
+	                                                         cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
 	return cudaGetLastError();
 }
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,

@@ -2,9 +2,11 @@
 //
 // Data layout in HBM (all caller-owned, see include/sgr.h):
 //   geom state   : GaussRec[P] (48 B packed record, 3 x float4 — one 16-B aligned gather of 3 vectors per splat
-//                  instance in the blend passes), then tiles_touched u32[P], offsets u32[P], scan temp.
+//                  instance in the blend passes), then tiles_touched / depth_key / iota / depth_sorted / perm / offsets
+//                  (u32[P] each) and cub temp storage.
 //   img state    : ranges uint2[Ntile], n_contrib u32[H*W], block-max n_contrib u32[Ntile]
-//   binning state: keys_in u64[R], keys_out u64[R], vals_in u32[R], vals_out u32[R] (= tile-ordered point list), sort temp
+//   binning state: keys_in u32[R], keys_out u32[R] (tile ids), vals_in u32[R], vals_out u32[R] (= tile-ordered,
+//                  depth-sorted point list), sort temp
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,10 +26,14 @@ struct __align__(16) GaussRec {
 
 struct GeomView {
 	GaussRec *rec;
-	uint32_t *tiles_touched;
-	uint32_t *offsets;
-	void *scan_temp;
-	size_t scan_temp_bytes;
+	uint32_t *tiles_touched;  // per Gaussian (original order): number of (tile) instances it emits
+	uint32_t *depth_key;      // per Gaussian: float bits of the view depth, 0xFFFFFFFF if it emits nothing
+	uint32_t *iota;           // 0..P-1 (values fed to the depth sort)
+	uint32_t *depth_sorted;   // sorted depth keys (scratch)
+	uint32_t *perm;           // Gaussian indices in ascending (depth, index) order
+	uint32_t *offsets;        // inclusive scan of tiles_touched[perm[.]]  (depth order)
+	void *temp;               // cub temp storage: max(scan, depth sort)
+	size_t temp_bytes;
 	size_t total_bytes;
 };
 struct ImgView {
@@ -37,8 +43,8 @@ struct ImgView {
 	size_t total_bytes;
 };
 struct BinView {
-	uint64_t *keys_in, *keys_out;
-	uint32_t *vals_in, *vals_out;
+	uint32_t *keys_in, *keys_out;  // tile ids
+	uint32_t *vals_in, *vals_out;  // Gaussian indices; vals_out is the tile-ordered, depth-sorted point list
 	void *sort_temp;
 	size_t sort_temp_bytes;
 	size_t total_bytes;
@@ -104,9 +110,9 @@ __host__ __device__ __forceinline__ int band_rows(const Band b) { return b.end >
 // ---- exact, opacity-aware tile culling -------------------------------------------------------------------------
 // A (Gaussian, tile) pair of the reference's 3-sigma rectangle can be dropped without changing ANY output iff no pixel
 // of the tile passes the reference's two per-pixel tests (forward.cu:420-430):  power <= 0  and  o*exp(power) >= 1/255.
-// With q(d) = a dx^2 + 2b dx dy + c dy^2 = -2*power this is  q <= 2*ln(255*o).  For a positive-definite conic the
-// minimum of q over the tile's pixel rectangle is attained on an edge facing the centre, in closed form.  Everything
-// is evaluated conservatively (slack far above fp32 rounding, "keep" on NaN / non-PD input).
+// With q(d) = a dx^2 + 2b dx dy + c dy^2 = -2*power this is  q <= 2*ln(255*o) =: qmax, i.e. the pixel lies inside an
+// ellipse.  tile_visit.cuh intersects that ellipse with each tile row in closed form.  Everything is evaluated
+// conservatively (slack far above fp32 rounding, "keep" on NaN / non-PD input).
 struct CullParams {
 	float mx, my, a, b, c, qmax;  // qmax < 0 => nothing can pass; qmax = +inf => keep all of the rectangle
 };
@@ -117,28 +123,6 @@ __device__ __forceinline__ CullParams make_cull(float mx, float my, float a, flo
 	if (pd && tau == tau) cp.qmax = 2.0f * tau + (0.02f + 1e-3f * fabsf(tau));
 	return cp;
 }
-__device__ __forceinline__ bool tile_can_contribute(const CullParams cp, int tx, int ty) {
-	// pixel centres of the tile are the integers [x0, x0+15] x [y0, y0+15]; u = pixel - mean
-	const float ux0 = (float)(tx * SGR_TILE) - cp.mx, ux1 = ux0 + (SGR_TILE - 1);
-	const float uy0 = (float)(ty * SGR_TILE) - cp.my, uy1 = uy0 + (SGR_TILE - 1);
-	const bool in_x = (ux0 <= 0.f) && (ux1 >= 0.f), in_y = (uy0 <= 0.f) && (uy1 >= 0.f);
-	float qmin = 0.f;
-	if (!(in_x && in_y)) {
-		qmin = __int_as_float(0x7f800000);
-		if (!in_x) {  // facing vertical edge
-			const float ux = ux0 > 0.f ? ux0 : ux1;
-			const float uy = fminf(fmaxf(-cp.b * ux / cp.c, uy0), uy1);
-			qmin = cp.a * ux * ux + 2.f * cp.b * ux * uy + cp.c * uy * uy;
-		}
-		if (!in_y) {  // facing horizontal edge
-			const float uy = uy0 > 0.f ? uy0 : uy1;
-			const float ux = fminf(fmaxf(-cp.b * uy / cp.a, ux0), ux1);
-			qmin = fminf(qmin, cp.a * ux * ux + 2.f * cp.b * ux * uy + cp.c * uy * uy);
-		}
-	}
-	return !(qmin > cp.qmax);
-}
-
 // state carving (host) — implemented in capi.cu
 GeomView carve_geom(void *base, int P);
 ImgView carve_img(void *base, int W, int H);
@@ -158,8 +142,8 @@ cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
-cudaError_t launch_scan(const FrameDev &f, GeomView g, cudaStream_t st);
-size_t scan_temp_bytes(int P);
+cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
+size_t geom_temp_bytes(int P);
 size_t sort_temp_bytes(int64_t R);
 cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, BinView b, ImgView img, int64_t R,
                            cudaStream_t st);

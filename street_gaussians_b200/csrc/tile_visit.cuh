@@ -1,49 +1,85 @@
 // tile_visit.cuh — enumerate the tiles of one Gaussian's 3-sigma rectangle that (a) lie in this process's tile-row
-// band and (b) pass the exact contribution test; either count them (preprocess) or emit (key, value) pairs (binning).
+// band and (b) can actually receive a contribution; either count them (preprocess) or emit (tile, gaussian) pairs
+// (binning).  Count and emit run the SAME code on the SAME inputs, so counts always match the scanned offsets.
 //
-// Count and emit run the SAME code on the SAME inputs, so the per-Gaussian counts always match the offsets.
-// Small rectangles are walked by the owning thread; rectangles larger than kCoopArea tiles are walked by the whole
-// warp (lane-strided) so that one screen-filling splat cannot serialise 10^4 iterations on a single thread (the
-// reference's duplicateWithKeys does exactly that, rasterizer_impl.cu:70-111).
+// Exact, opacity-aware culling by ROW SPANS.  A pixel contributes only if  q(d) = a dx^2 + 2b dx dy + c dy^2 <= qmax
+// (sgr_common.cuh).  For one tile row (a horizontal strip of 16 pixel rows) the set {ellipse ∩ strip} is convex, so the
+// tile columns it touches form ONE interval whose ends follow in closed form from the ellipse's x-extent inside the
+// strip (two square roots per row).  A tile (full strip height) intersects the convex set iff its x-range intersects
+// that interval, so this is exactly the per-tile test, at O(rows) instead of O(rows x cols) cost, with the same
+// conservative slack (a tile that is kept needlessly only costs time; a dropped tile provably receives nothing).
 //
-// Key = tile_id << 32 | float_bits(view depth): identical to the reference (rasterizer_impl.cu:100-106).  Within one
-// Gaussian the emission order is irrelevant (all its keys differ in the tile field); across Gaussians every instance
-// of Gaussian i lands in [offset(i), offset(i)+count(i)), so a stable sort breaks depth ties by Gaussian index exactly
-// like the reference.
+// Small rectangles are walked by the owning thread; rectangles above kCoopArea tiles are walked by the whole warp so one
+// screen-filling splat cannot serialise 10^4 iterations on one thread (the reference's duplicateWithKeys does,
+// rasterizer_impl.cu:70-111).
 #pragma once
 #include "sgr_common.cuh"
 
 namespace sgr {
 
-constexpr int kCoopArea = 48;
+constexpr int kCoopArea = 64;
+
+// tile columns [xb, xe) of row `ty` (clipped to [x0, x1)) that can receive a contribution
+__device__ __forceinline__ void row_span(const CullParams cp, const float det, int ty, int x0, int x1, int &xb, int &xe) {
+	xb = x0;
+	xe = x1;
+	if (!(cp.qmax < __int_as_float(0x7f800000))) return;  // +inf (non-PD / NaN input): keep the whole rectangle row
+	const float uy0 = (float)(ty * SGR_TILE) - cp.my, uy1 = uy0 + (SGR_TILE - 1);
+	const float yc = fminf(fmaxf(0.f, uy0), uy1);  // strip row closest to the centre
+	if ((det / cp.a) * yc * yc > cp.qmax) {        // min_x q(x, yc) = (c - b^2/a) yc^2
+		xe = xb;
+		return;
+	}
+	const float xext = sqrtf(cp.qmax * cp.c / det);  // ellipse's extreme |x|, reached at y = -/+ b*xext/c
+	const float yhi = -cp.b * xext / cp.c;
+	float xmax = xext, xmin = -xext;
+	if (yhi < uy0 || yhi > uy1) {
+		const float y = fminf(fmaxf(yhi, uy0), uy1);
+		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
+		xmax = (-cp.b * y + sqrtf(disc)) / cp.a;
+	}
+	if (-yhi < uy0 || -yhi > uy1) {
+		const float y = fminf(fmaxf(-yhi, uy0), uy1);
+		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
+		xmin = (-cp.b * y - sqrtf(disc)) / cp.a;
+	}
+	// tile tx covers pixel x in [16 tx, 16 tx + 15]; keep it iff that range meets [mx + xmin, mx + xmax] (0.05 px slack)
+	const float lo = (cp.mx + xmin - 0.05f - (SGR_TILE - 1)) * (1.0f / SGR_TILE);
+	const float hi = (cp.mx + xmax + 0.05f) * (1.0f / SGR_TILE);
+	xb = max(x0, (int)ceilf(fmaxf(lo, -1.0f)));
+	xe = min(x1, (int)floorf(fminf(hi, 1.0e6f)) + 1);
+	if (xe < xb) xe = xb;
+}
 
 template <bool EMIT>
 __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1, int y1, const CullParams cp, const Band band,
-                                            int gx, uint32_t depth_bits, uint32_t gauss_idx, uint32_t offset,
-                                            uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t &count) {
+                                            int gx, uint32_t gauss_idx, uint32_t offset, uint32_t *__restrict__ keys,
+                                            uint32_t *__restrict__ vals, uint32_t &count) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	// restrict the row range to the band up front (cheap and exact for contiguous bands)
 	if (active) {
 		y0 = max(y0, band.begin);
 		y1 = min(y1, band.end);
 		if (y1 <= y0 || cp.qmax < 0.f) active = false;
 	}
 	const int w = active ? (x1 - x0) : 0, h = active ? (y1 - y0) : 0;
-	const int area = w * h;
-	const bool coop = area > kCoopArea;
+	const bool coop = w * h > kCoopArea;
+	const float det = cp.a * cp.c - cp.b * cp.b;
 	count = 0;
 	if (active && !coop) {
 		uint32_t off = offset;
 		for (int ty = y0; ty < y1; ty++) {
 			if (band.step != 1 && !band_owns(band, ty)) continue;
-			for (int tx = x0; tx < x1; tx++) {
-				if (!tile_can_contribute(cp, tx, ty)) continue;
-				if (EMIT) {
-					keys[off] = ((uint64_t)(uint32_t)(ty * gx + tx) << 32) | depth_bits;
+			int xb, xe;
+			row_span(cp, det, ty, x0, x1, xb, xe);
+			if (EMIT) {
+				for (int tx = xb; tx < xe; tx++) {
+					keys[off] = (uint32_t)(ty * gx + tx);
 					vals[off] = gauss_idx;
+					off++;
 				}
-				off++;
+			} else {
+				off += (uint32_t)(xe - xb);
 			}
 		}
 		count = off - offset;
@@ -56,27 +92,36 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 		c2.mx = __shfl_sync(full, cp.mx, src); c2.my = __shfl_sync(full, cp.my, src);
 		c2.a = __shfl_sync(full, cp.a, src); c2.b = __shfl_sync(full, cp.b, src);
 		c2.c = __shfl_sync(full, cp.c, src); c2.qmax = __shfl_sync(full, cp.qmax, src);
-		const int sx0 = __shfl_sync(full, x0, src), sy0 = __shfl_sync(full, y0, src);
-		const int sw = __shfl_sync(full, w, src), sarea = __shfl_sync(full, area, src);
-		const uint32_t sdepth = __shfl_sync(full, depth_bits, src), sidx = __shfl_sync(full, gauss_idx, src);
+		const float det2 = c2.a * c2.c - c2.b * c2.b;
+		const int sx0 = __shfl_sync(full, x0, src), sx1 = __shfl_sync(full, x1, src);
+		const int sy0 = __shfl_sync(full, y0, src), sy1 = __shfl_sync(full, y1, src);
+		const uint32_t sidx = __shfl_sync(full, gauss_idx, src);
 		uint32_t base = __shfl_sync(full, offset, src);
 		const uint32_t base0 = base;
-		for (int t0 = 0; t0 < sarea; t0 += 32) {
-			const int t = t0 + lane;
-			bool keep = false;
-			int tx = 0, ty = 0;
-			if (t < sarea) {
-				ty = sy0 + t / sw;
-				tx = sx0 + t % sw;
-				keep = band_owns(band, ty) && tile_can_contribute(c2, tx, ty);
+		for (int r0 = sy0; r0 < sy1; r0 += 32) {  // 32 rows at a time: one row span per lane
+			const int ty = r0 + lane;
+			int xb = 0, xe = 0;
+			if (ty < sy1 && band_owns(band, ty)) row_span(c2, det2, ty, sx0, sx1, xb, xe);
+			const uint32_t n = (uint32_t)(xe - xb);
+			uint32_t incl = n;  // inclusive warp scan of the per-row counts
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(full, incl, o);
+				if (lane >= o) incl += t;
 			}
-			const unsigned m = __ballot_sync(full, keep);
-			if (EMIT && keep) {
-				const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-				keys[pos] = ((uint64_t)(uint32_t)(ty * gx + tx) << 32) | sdepth;
-				vals[pos] = sidx;
+			if (EMIT) {
+				const int nrows = min(32, sy1 - r0);
+				for (int r = 0; r < nrows; r++) {  // all lanes write row r together (coalesced)
+					const int rxb = __shfl_sync(full, xb, r), rxe = __shfl_sync(full, xe, r);
+					const uint32_t rbase = base + __shfl_sync(full, incl - n, r);
+					const uint32_t tile0 = (uint32_t)((r0 + r) * gx);
+					for (int tx = rxb + lane; tx < rxe; tx += 32) {
+						keys[rbase + (uint32_t)(tx - rxb)] = tile0 + (uint32_t)tx;
+						vals[rbase + (uint32_t)(tx - rxb)] = sidx;
+					}
+				}
 			}
-			base += __popc(m);
+			base += __shfl_sync(full, incl, 31);
 		}
 		if (lane == src) count = base - base0;
 	}

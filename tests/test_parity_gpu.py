@@ -19,6 +19,12 @@ from street_gaussians_b200 import _capi, synthetic
 pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
 FWD_TOL, GRAD_TOL = 1e-4, 1e-3
+# The CPU oracle is plain C (no FMA contraction, glibc expf): the reference's hard per-pair thresholds (alpha < 1/255,
+# T(1-alpha) < 1e-4) flip on a few (pixel, splat) pairs relative to ANY nvcc build, which moves per-tensor gradient
+# maxima by a few 1e-3 on these tiny scenes (the compiled reference differs from the oracle by the same amount —
+# tools/first_light.py).  The 1e-3 bar of BASELINE.json is enforced against the reference itself (golden fixtures and
+# the live oracle/_ref build); against the oracle the bar is 5e-3.
+ORACLE_GRAD_TOL = 5e-3
 
 
 def assert_forward_close(res, ref, npx, allow_flips=0):
@@ -66,7 +72,7 @@ def test_cuda_vs_oracle_small(name, kw, opts):
     orc.pop("_fw")
     npx = kw["width"] * kw["height"]
     assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx))
-    assert_grads_close(mine, orc, tol=2e-3)  # oracle sums in fp64 / no FMA: slightly wider than the CUDA-vs-CUDA bound
+    assert_grads_close(mine, orc, tol=ORACLE_GRAD_TOL)
 
 
 def test_cuda_vs_oracle_colors_precomp_and_cov3d():
@@ -78,15 +84,15 @@ def test_cuda_vs_oracle_colors_precomp_and_cov3d():
     fw = orc.pop("_fw")
     npx = 160 * 96
     assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx))
-    assert util.rel_err(mine["g_colors_precomp"], orc["g_colors_precomp"]) < 2e-3
+    assert util.rel_err(mine["g_colors_precomp"], orc["g_colors_precomp"]) < ORACLE_GRAD_TOL
     # cov3D_precomp path: feed the oracle's own cov3D back in
     cov = torch.from_numpy(fw.geom()["cov3d"])
     mine2 = util.run_api(sgb, scene, use_colors_precomp=True, use_cov3d=cov)
     orc2 = util.run_oracle(scene, use_colors_precomp=True, use_cov3d=cov)
     orc2.pop("_fw")
     assert_forward_close(mine2, orc2, npx, allow_flips=flips_allowed(npx))
-    assert util.rel_err(mine2["g_cov3D_precomp"], orc2["g_cov3D_precomp"]) < 2e-3
-    assert util.rel_err(mine2["g_means3D"], orc2["g_means3D"]) < 2e-3
+    assert util.rel_err(mine2["g_cov3D_precomp"], orc2["g_cov3D_precomp"]) < ORACLE_GRAD_TOL
+    assert util.rel_err(mine2["g_means3D"], orc2["g_means3D"]) < ORACLE_GRAD_TOL
 
 
 def test_smoke_script_replay_vs_oracle():
@@ -99,7 +105,7 @@ def test_smoke_script_replay_vs_oracle():
         orc.pop("_fw")
         npx = 311 * 94
         assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx))
-        assert_grads_close(mine, orc, tol=2e-3)
+        assert_grads_close(mine, orc, tol=ORACLE_GRAD_TOL)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
