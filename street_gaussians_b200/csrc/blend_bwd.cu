@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
                                                         float *__restrict__ grad2d, float *__restrict__ dL_dsemantics) {
 	__shared__ float4 s_q0[2][kBwdBatch];
 	__shared__ float4 s_q1[2][kBwdBatch];
-	__shared__ float2 s_q2[2][kBwdBatch];
+	__shared__ float4 s_q2[2][kBwdBatch];
 	__shared__ uint32_t s_id[2][kBwdBatch];
 	__shared__ float s_part[8][kBwdBatch][kNComp];
 	__shared__ unsigned long long s_mask[8];
@@ -81,6 +81,9 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 	const int tile = tile_y * f.gx + tile_x;
 	const int n_eff = (int)tile_max_contrib[tile];
 	if (n_eff == 0) return;
+	const bool use_mask = f.P < (1 << 24);  // point-list value = warp mask << 24 | index (tile_visit.cuh)
+	const uint32_t idx_mask = use_mask ? kIdxMask : 0xffffffffu;
+	const uint32_t my_bit = use_mask ? (1u << (24 + warp)) : 0u;
 	const int px = tile_x * SGR_TILE + (warp & 1) * 8 + (lane & 7);
 	const int py = tile_y * SGR_TILE + (warp >> 1) * 4 + (lane >> 3);
 	const bool inside = px < f.W && py < f.H;
@@ -121,13 +124,13 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 		const int idx = n_eff - b * kBwdBatch - 1 - ld_slot;
 		if (idx >= 0) {
 			rid = point_list[list0 + idx];
-			if (ld_part < 3) rq = reinterpret_cast<const float4 *>(rec + rid)[ld_part];
+			if (ld_part < 3) rq = reinterpret_cast<const float4 *>(rec + (rid & idx_mask))[ld_part];
 		}
 	};
 	auto stash = [&](int buf) {
 		if (ld_part == 0) s_q0[buf][ld_slot] = rq;
 		else if (ld_part == 1) s_q1[buf][ld_slot] = rq;
-		else if (ld_part == 2) s_q2[buf][ld_slot] = make_float2(rq.x, rq.y);
+		else if (ld_part == 2) s_q2[buf][ld_slot] = rq;
 		else s_id[buf][ld_slot] = rid;
 	};
 	fetch(0);
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 		unsigned long long wmask = 0ull;
 		for (int j = 0; j < cnt; j++) {
 			const int contributor = hi - 1 - j;  // 0-based list index of this slot
+			if (my_bit != 0u && (s_id[buf][j] & my_bit) == 0u) continue;  // warp-uniform skip: block cannot receive anything
 			bool valid = contributor < last_contributor;
 			float v[16];
 #pragma unroll
@@ -152,15 +156,19 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 				const float4 q1 = s_q1[buf][j];
 				const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
 				const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
-				const float G = expf(power);
-				const float alpha = fminf(0.99f, q1.y * G);
-				valid = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+				valid = !(power > 0.0f) && !(power < q1.z);  // q1.z: conservative bound below which alpha < 1/255 for sure
+				float G = 0.f, alpha = 0.f;
 				if (valid) {
-					const float2 q2 = s_q2[buf][j];
+					G = expf(power);
+					alpha = fminf(0.99f, q1.y * G);
+					valid = !(alpha < 1.0f / 255.0f);
+				}
+				if (valid) {
+					const float4 q2 = s_q2[buf][j];
 					T = T / (1.f - alpha);
 					const float dchannel_dcolor = alpha * T;
 					float dL_dopa = 0.0f;
-					const float col[3] = {q1.w, q2.x, q2.y};
+					const float col[3] = {q2.x, q2.y, q2.z};
 #pragma unroll
 					for (int ch = 0; ch < 3; ch++) {
 						const float c = col[ch];
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 						v[7 + ch] = dchannel_dcolor * dL_dchannel;
 					}
 					if (SCH > 0) {
-						const float *sp = semantics + (size_t)s_id[buf][j] * f.S;
+						const float *sp = semantics + (size_t)(s_id[buf][j] & idx_mask) * f.S;
 #pragma unroll
 						for (int ch = 0; ch < SCH; ch++)
 							if (ch < f.S) {
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 							}
 						sem_w = dchannel_dcolor;
 					}
-					const float c_d = q1.z;
+					const float c_d = q1.w;
 					accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
 					last_depth = c_d;
 					dL_dopa += (c_d - accum_depth_rec) * dL_dpixel_depth;
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 			wmask |= 1ull << j;
 			if (SCH > 0) {
 				// feature channels: plain butterfly per channel, one global atomic per (warp, splat, channel)
-				const uint32_t gid = s_id[buf][j];
+				const uint32_t gid = s_id[buf][j] & idx_mask;
 #pragma unroll
 				for (int ch = 0; ch < SCH; ch++)
 					if (ch < f.S) {
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(const FrameDev f, const 
 						a2 += s_part[w][slot][c0 + 2];
 					}
 				if (live) {
-					float *dst = grad2d + (size_t)s_id[buf][slot] * kNComp + c0;
+					float *dst = grad2d + (size_t)(s_id[buf][slot] & idx_mask) * kNComp + c0;
 					atomicAdd(dst, a0);
 					atomicAdd(dst + 1, a1);
 					if (c0 + 2 < 11) atomicAdd(dst + 2, a2);

@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
                                                         float *__restrict__ out_sem, const int sem_ch0, const int sem_only) {
 	__shared__ float4 s_q0[2][kFwdBatch];
 	__shared__ float4 s_q1[2][kFwdBatch];
-	__shared__ float2 s_q2[2][kFwdBatch];
-	__shared__ uint32_t s_id[SCH > 0 ? 2 : 1][SCH > 0 ? kFwdBatch : 1];
+	__shared__ float4 s_q2[2][kFwdBatch];
+	__shared__ uint32_t s_id[2][kFwdBatch];  // warp mask << 24 | Gaussian index
 	__shared__ uint32_t s_max;
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -39,6 +39,11 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 	const size_t HW = (size_t)f.W * f.H;
 	const size_t pix_id = (size_t)f.W * py + px;
 	const float2 pixf = make_float2((float)px, (float)py);
+
+	// point-list values carry the 8-bit warp mask above the 24-bit index when P < 2^24 (tile_visit.cuh)
+	const bool use_mask = f.P < (1 << 24);
+	const uint32_t idx_mask = use_mask ? kIdxMask : 0xffffffffu;
+	const uint32_t my_bit = use_mask ? (1u << (24 + warp)) : 0u;
 
 	const uint2 range = ranges[tile];
 	const int n = (int)(range.y - range.x);
@@ -61,13 +66,13 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 		const int k = b * kFwdBatch + tid;
 		if (k < n) {
 			rid = point_list[range.x + k];
-			const GaussRec *p = rec + rid;
+			const GaussRec *p = rec + (rid & idx_mask);
 			r0 = p->q0; r1 = p->q1; r2 = p->q2;
 		}
 	};
 	auto stash = [&](int buf) {
-		s_q0[buf][tid] = r0; s_q1[buf][tid] = r1; s_q2[buf][tid] = make_float2(r2.x, r2.y);
-		if (SCH > 0) s_id[buf][tid] = rid;
+		s_q0[buf][tid] = r0; s_q1[buf][tid] = r1; s_q2[buf][tid] = r2;
+		s_id[buf][tid] = rid;
 	};
 	if (nb > 0) { fetch(0); stash(0); }
 
@@ -80,11 +85,14 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 		const int cnt = min(kFwdBatch, n - b * kFwdBatch);
 		const uint32_t pos0 = (uint32_t)(b * kFwdBatch);
 		for (int j = 0; !done && j < cnt; j++) {
+			const uint32_t v = s_id[buf][j];
+			if (my_bit != 0u && (v & my_bit) == 0u) continue;  // warp-uniform: this 8x4 block cannot receive anything
 			const float4 q0 = s_q0[buf][j];
 			const float4 q1 = s_q1[buf][j];
 			const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
 			const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
 			if (power > 0.0f) continue;
+			if (power < q1.z) continue;  // conservative: alpha < 1/255 for sure, skip the expf (exact test still below)
 			const float alpha = fminf(0.99f, q1.y * expf(power));
 			if (alpha < 1.0f / 255.0f) continue;
 			const float test_T = T * (1 - alpha);
@@ -92,18 +100,18 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 				done = true;
 				continue;
 			}
-			const float2 q2 = s_q2[buf][j];
-			C0 += q1.w * alpha * T;
-			C1 += q2.x * alpha * T;
-			C2 += q2.y * alpha * T;
+			const float4 q2 = s_q2[buf][j];
+			C0 += q2.x * alpha * T;
+			C1 += q2.y * alpha * T;
+			C2 += q2.z * alpha * T;
 			if (SCH > 0) {
-				const float *sp = semantics + (size_t)s_id[buf][j] * f.S + sem_ch0;
+				const float *sp = semantics + (size_t)(v & idx_mask) * f.S + sem_ch0;
 #pragma unroll
 				for (int c = 0; c < SCH; c++)
 					if (c < nsem) sem[c] += __ldg(sp + c) * alpha * T;
 			}
 			weight += alpha * T;
-			Dacc += q1.z * alpha * T;
+			Dacc += q1.w * alpha * T;
 			T = test_T;
 			last_contributor = pos0 + (uint32_t)j + 1u;
 		}

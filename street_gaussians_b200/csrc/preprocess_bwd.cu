@@ -8,6 +8,10 @@
 //     reference's 304 B/Gaussian of torch::zeros (rasterize_points.cu:166-176) disappears;
 //   * dL/dmean3D is accumulated in registers across the three contributions and stored once (the reference does
 //     one store + two read-modify-writes + one more inside the SH routine).
+//   * SH coefficients in / SH gradients out are staged through shared memory per warp: the 32 Gaussians of a warp own
+//     one contiguous 32 x M x 3 float block of `shs` / `dL_dsh`, which the warp moves with fully coalesced 16-B accesses
+//     (rows padded to 49 floats in smem so the per-thread row walks are bank-conflict free).  The direct per-thread
+//     version (48 strided scalar loads + 48 strided scalar stores per Gaussian) ran at ~1.9 TB/s; see DESIGN.md §5.
 // Formulas and evaluation order follow the reference so gradients agree to fp32 rounding.
 #include "sgr_common.cuh"
 
@@ -29,37 +33,77 @@ __device__ __forceinline__ M3 rot_colmajor(const float4 q) {
 	return R;
 }
 
+constexpr int kShRow = 49;  // padded smem row (floats) for up to 16 x 3 SH coefficients
+
+template <bool STAGED>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const FrameDev f, const float *__restrict__ means3D, const float *__restrict__ shs, const float *__restrict__ colors_precomp,
     const float *__restrict__ scales, const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
     const int32_t *__restrict__ radii, const GaussRec *__restrict__ rec, const float *__restrict__ grad2d,
     float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D, float *__restrict__ dL_dsh, float *__restrict__ dL_dcolors,
     float *__restrict__ dL_dopacity, float *__restrict__ dL_dscales, float *__restrict__ dL_drot, float *__restrict__ dL_dcov3D) {
+	extern __shared__ float s_sh[];  // [warps][32][kShRow] when STAGED
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= f.P) return;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool in_range = idx < f.P;
 	const size_t i = (size_t)idx;
 	const int nsh = f.M * 3;
-	const bool visible = radii[idx] > 0;
+	const bool visible = in_range && radii[idx] > 0;
+	float *srow = STAGED ? (s_sh + ((size_t)warp * 32 + lane) * kShRow) : nullptr;
 
-	const float4 g0 = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
-	const float4 g1 = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
-	const float4 g2 = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
+	if (STAGED && shs != nullptr) {
+		// coalesced stage-in of this warp's 32 x nsh block (visible rows only)
+		const unsigned vis_mask = __ballot_sync(0xffffffffu, visible);
+		const size_t g0 = (size_t)(blockIdx.x * blockDim.x + warp * 32);
+		const int rows = (int)min((size_t)32, g0 < (size_t)f.P ? (size_t)f.P - g0 : (size_t)0);
+		float *wbase = s_sh + (size_t)warp * 32 * kShRow;
+		if ((nsh & 3) == 0) {
+			const float4 *src = reinterpret_cast<const float4 *>(shs + g0 * nsh);
+			const int n4 = rows * nsh / 4;
+			for (int e = lane; e < n4; e += 32) {
+				const int row = (4 * e) / nsh, col = (4 * e) - row * nsh;
+				if ((vis_mask >> row) & 1u) {
+					const float4 v = __ldg(src + e);
+					float *d = wbase + row * kShRow + col;
+					d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+				}
+			}
+		} else {
+			const float *src = shs + g0 * nsh;
+			for (int e = lane; e < rows * nsh; e += 32) {
+				const int row = e / nsh, col = e - row * nsh;
+				if ((vis_mask >> row) & 1u) wbase[row * kShRow + col] = __ldg(src + e);
+			}
+		}
+		__syncwarp();
+	}
 
-	dL_dmeans2D[3 * i] = g0.x; dL_dmeans2D[3 * i + 1] = g0.y; dL_dmeans2D[3 * i + 2] = g0.z;
-	dL_dopacity[i] = g1.z;
-	if (dL_dcolors) { dL_dcolors[3 * i] = g1.w; dL_dcolors[3 * i + 1] = g2.x; dL_dcolors[3 * i + 2] = g2.y; }
+	float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, g2v = g0v;
+	if (in_range) {
+		g0v = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
+		g1v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
+		g2v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
+		dL_dmeans2D[3 * i] = g0v.x; dL_dmeans2D[3 * i + 1] = g0v.y; dL_dmeans2D[3 * i + 2] = g0v.z;
+		dL_dopacity[i] = g1v.z;
+		if (dL_dcolors) { dL_dcolors[3 * i] = g1v.w; dL_dcolors[3 * i + 1] = g2v.x; dL_dcolors[3 * i + 2] = g2v.y; }
+	}
+	const float4 g0 = g0v, g1 = g1v, g2 = g2v;
 
-	if (!visible) {
+	if (in_range && !visible) {
 		dL_dmeans3D[3 * i] = 0.f; dL_dmeans3D[3 * i + 1] = 0.f; dL_dmeans3D[3 * i + 2] = 0.f;
 		if (dL_dscales) { dL_dscales[3 * i] = 0.f; dL_dscales[3 * i + 1] = 0.f; dL_dscales[3 * i + 2] = 0.f; }
 		if (dL_drot) reinterpret_cast<float4 *>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 		if (dL_dcov3D)
 			for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
-		if (dL_dsh)
-			for (int k = 0; k < nsh; k++) dL_dsh[i * nsh + k] = 0.f;
-		return;
+		if (dL_dsh) {
+			if (STAGED) {
+				for (int k = 0; k < nsh; k++) srow[k] = 0.f;
+			} else {
+				for (int k = 0; k < nsh; k++) dL_dsh[i * nsh + k] = 0.f;
+			}
+		}
 	}
-
+	if (visible) {
 	const float *view = f.view, *proj = f.proj;
 	const float3 mean = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
 
@@ -171,9 +215,9 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 
 	// ---- SH backward (reference backward.cu:20-139) ----
 	if (shs != nullptr) {
-		const float *sh = shs + i * nsh;
-		float *dsh = dL_dsh + i * nsh;
-		const uint32_t clamp_bits = __float_as_uint(rec[idx].q2.z);
+		const float *sh = STAGED ? srow : shs + i * nsh;
+		float *dsh = STAGED ? srow : dL_dsh + i * nsh;
+		const uint32_t clamp_bits = __float_as_uint(rec[idx].q2.w);
 		const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
 		const float3 dir_orig = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
 		const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -189,7 +233,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 		for (int k = ncoef * 3; k < nsh; k++) dsh[k] = 0.f;
 #pragma unroll
 		for (int ch = 0; ch < 3; ch++) {
-#define SHC(k) __ldg(sh + (k) * 3 + ch)
+			// all coefficients of this channel are read before any gradient is written: sh and dsh may alias (staged rows)
+			float cf[16];
+#pragma unroll
+			for (int k = 0; k < 16; k++) cf[k] = k < ncoef ? sh[k * 3 + ch] : 0.f;
+#define SHC(k) cf[k]
 #define DSH(k) dsh[(k) * 3 + ch]
 			const float g = dRGB[ch];
 			float dx = 0.f, dy = 0.f, dz = 0.f;
@@ -261,6 +309,30 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 #undef D_
 		reinterpret_cast<float4 *>(dL_drot)[i] = dq;
 	}
+	}  // visible
+
+	if (STAGED && dL_dsh != nullptr) {
+		// coalesced stage-out of the warp's 32 x nsh gradient block (rows of culled Gaussians were zero-filled above)
+		__syncwarp();
+		const size_t g0s = (size_t)(blockIdx.x * blockDim.x + warp * 32);
+		const int rows = (int)min((size_t)32, g0s < (size_t)f.P ? (size_t)f.P - g0s : (size_t)0);
+		const float *wbase = s_sh + (size_t)warp * 32 * kShRow;
+		if ((nsh & 3) == 0) {
+			float4 *dst = reinterpret_cast<float4 *>(dL_dsh + g0s * nsh);
+			const int n4 = rows * nsh / 4;
+			for (int e = lane; e < n4; e += 32) {
+				const int row = (4 * e) / nsh, col = (4 * e) - row * nsh;
+				const float *sp = wbase + row * kShRow + col;
+				dst[e] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+			}
+		} else {
+			float *dst = dL_dsh + g0s * nsh;
+			for (int e = lane; e < rows * nsh; e += 32) {
+				const int row = e / nsh, col = e - row * nsh;
+				dst[e] = wbase[row * kShRow + col];
+			}
+		}
+	}
 }
 
 cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
@@ -270,9 +342,23 @@ cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const
                                   float *dL_dscales, float *dL_drot, float *dL_dcov3D, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
 	(void)colors_precomp;
-	preprocess_bwd_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii,
-	                                                         g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity,
-	                                                         dL_dscales, dL_drot, dL_dcov3D);
+	const bool staged = shs != nullptr && f.M <= 16;  // rows of up to 48 floats fit the padded smem row
+	if (staged) {
+		const size_t smem = (size_t)8 * 32 * kShRow * sizeof(float);  // 50,176 B: above the 48 KB static limit -> opt in
+		static bool configured = false;
+		if (!configured) {
+			cudaError_t e = cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return e;
+			configured = true;
+		}
+		preprocess_bwd_kernel<true><<<(f.P + 255) / 256, 256, smem, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
+		                                                                  radii, g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+		                                                                  dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
+	} else {
+		preprocess_bwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
+		                                                               radii, g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+		                                                               dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
+	}
 	return cudaGetLastError();
 }
 

@@ -19,7 +19,9 @@
 namespace sgr {
 
 // 48-byte per-Gaussian record written by preprocess_fwd and gathered by both blend passes.
-//   q0 = (pix.x, pix.y, conic.xx, conic.xy)   q1 = (conic.yy, opacity, view depth, r)   q2 = (g, b, bits(clamped), unused)
+//   q0 = (pix.x, pix.y, conic.xx, conic.xy)   q1 = (conic.yy, opacity, power_min, view depth)   q2 = (r, g, b, bits(clamped))
+// power_min = -qmax/2 (conservative): a pair with power < power_min cannot reach alpha >= 1/255, so the blend loops skip
+// it before evaluating expf; pairs that pass still take the reference's exact alpha test.
 struct __align__(16) GaussRec {
 	float4 q0, q1, q2;
 };
@@ -129,6 +131,8 @@ ImgView carve_img(void *base, int W, int H);
 BinView carve_bin(void *base, int64_t R);
 
 // kernel launchers (host) — one per translation unit
+constexpr uint32_t kIdxMask = 0x00ffffffu;  // point-list value = warp mask << 24 | Gaussian index (when P < 2^24)
+
 struct FrameDev {  // SgrFrame + derived values, passed by value to kernels
 	int P, D, M, S, W, H, gx, gy;
 	float tanx, tany, fx, fy, mod;

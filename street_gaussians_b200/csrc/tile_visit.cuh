@@ -9,6 +9,10 @@
 // that interval, so this is exactly the per-tile test, at O(rows) instead of O(rows x cols) cost, with the same
 // conservative slack (a tile that is kept needlessly only costs time; a dropped tile provably receives nothing).
 //
+// At emission the value carries, above the 24-bit Gaussian index, an 8-bit mask of the tile's eight 8x4-pixel blocks that
+// can receive a contribution (same closed form on 4-pixel strips); the blend kernels map one warp to each block and
+// skip a splat outright when their bit is clear.  (Only when P < 2^24; otherwise the value is the plain index.)
+//
 // Small rectangles are walked by the owning thread; rectangles above kCoopArea tiles are walked by the whole warp so one
 // screen-filling splat cannot serialise 10^4 iterations on one thread (the reference's duplicateWithKeys does,
 // rasterizer_impl.cu:70-111).
@@ -19,20 +23,14 @@ namespace sgr {
 
 constexpr int kCoopArea = 64;
 
-// tile columns [xb, xe) of row `ty` (clipped to [x0, x1)) that can receive a contribution
-__device__ __forceinline__ void row_span(const CullParams cp, const float det, int ty, int x0, int x1, int &xb, int &xe) {
-	xb = x0;
-	xe = x1;
-	if (!(cp.qmax < __int_as_float(0x7f800000))) return;  // +inf (non-PD / NaN input): keep the whole rectangle row
-	const float uy0 = (float)(ty * SGR_TILE) - cp.my, uy1 = uy0 + (SGR_TILE - 1);
-	const float yc = fminf(fmaxf(0.f, uy0), uy1);  // strip row closest to the centre
-	if ((det / cp.a) * yc * yc > cp.qmax) {        // min_x q(x, yc) = (c - b^2/a) yc^2
-		xe = xb;
-		return;
-	}
-	const float xext = sqrtf(cp.qmax * cp.c / det);  // ellipse's extreme |x|, reached at y = -/+ b*xext/c
-	const float yhi = -cp.b * xext / cp.c;
-	float xmax = xext, xmin = -xext;
+// x-extent [xmin, xmax] (relative to the centre) of {ellipse q <= qmax} ∩ {uy0 <= y <= uy1}; false if empty.
+// Requires a finite qmax and a positive-definite conic (make_cull guarantees both when qmax is finite).
+__device__ __forceinline__ bool strip_xrange(const CullParams cp, const float det, const float xext, const float yhi, float uy0,
+                                             float uy1, float &xmin, float &xmax) {
+	const float yc = fminf(fmaxf(0.f, uy0), uy1);          // strip row closest to the centre
+	if ((det / cp.a) * yc * yc > cp.qmax) return false;    // min_x q(x, yc) = (c - b^2/a) yc^2
+	xmax = xext;
+	xmin = -xext;
 	if (yhi < uy0 || yhi > uy1) {
 		const float y = fminf(fmaxf(yhi, uy0), uy1);
 		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
@@ -43,6 +41,31 @@ __device__ __forceinline__ void row_span(const CullParams cp, const float det, i
 		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
 		xmin = (-cp.b * y - sqrtf(disc)) / cp.a;
 	}
+	return true;
+}
+
+struct EllipseAux {
+	float det, xext, yhi;  // det of the conic; extreme |x| of the ellipse, reached at y = -/+ yhi
+};
+__device__ __forceinline__ EllipseAux ellipse_aux(const CullParams cp) {
+	EllipseAux e;
+	e.det = cp.a * cp.c - cp.b * cp.b;
+	e.xext = sqrtf(cp.qmax * cp.c / e.det);
+	e.yhi = -cp.b * e.xext / cp.c;
+	return e;
+}
+
+// tile columns [xb, xe) of row `ty` (clipped to [x0, x1)) that can receive a contribution
+__device__ __forceinline__ void row_span(const CullParams cp, const EllipseAux ea, int ty, int x0, int x1, int &xb, int &xe) {
+	xb = x0;
+	xe = x1;
+	if (!(cp.qmax < __int_as_float(0x7f800000))) return;  // +inf (non-PD / NaN input): keep the whole rectangle row
+	const float uy0 = (float)(ty * SGR_TILE) - cp.my;
+	float xmin, xmax;
+	if (!strip_xrange(cp, ea.det, ea.xext, ea.yhi, uy0, uy0 + (SGR_TILE - 1), xmin, xmax)) {
+		xe = xb;
+		return;
+	}
 	// tile tx covers pixel x in [16 tx, 16 tx + 15]; keep it iff that range meets [mx + xmin, mx + xmax] (0.05 px slack)
 	const float lo = (cp.mx + xmin - 0.05f - (SGR_TILE - 1)) * (1.0f / SGR_TILE);
 	const float hi = (cp.mx + xmax + 0.05f) * (1.0f / SGR_TILE);
@@ -51,10 +74,30 @@ __device__ __forceinline__ void row_span(const CullParams cp, const float det, i
 	if (xe < xb) xe = xb;
 }
 
+// Which of the tile's eight 8x4-pixel blocks (= the eight warps of the blend kernels: bit 2*sr + half, sr = pixel-row
+// quarter, half = left/right 8 columns) can receive a contribution.  Same closed form on 4-pixel-high strips.
+__device__ __forceinline__ uint32_t warp_mask(const CullParams cp, const EllipseAux ea, int tx, int ty) {
+	if (!(cp.qmax < __int_as_float(0x7f800000))) return 0xffu;
+	const float ux0 = (float)(tx * SGR_TILE) - cp.mx;  // relative x of the tile's first pixel column
+	uint32_t m = 0;
+#pragma unroll
+	for (int sr = 0; sr < 4; sr++) {
+		const float uy0 = (float)(ty * SGR_TILE + 4 * sr) - cp.my;
+		float xmin, xmax;
+		if (!strip_xrange(cp, ea.det, ea.xext, ea.yhi, uy0, uy0 + 3.f, xmin, xmax)) continue;
+		xmin -= 0.05f;
+		xmax += 0.05f;
+		const bool left = (ux0 <= xmax) && (ux0 + 7.f >= xmin);
+		const bool right = (ux0 + 8.f <= xmax) && (ux0 + 15.f >= xmin);
+		m |= (left ? 1u : 0u) << (2 * sr) | (right ? 1u : 0u) << (2 * sr + 1);
+	}
+	return m;
+}
+
 template <bool EMIT>
 __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1, int y1, const CullParams cp, const Band band,
                                             int gx, uint32_t gauss_idx, uint32_t offset, uint32_t *__restrict__ keys,
-                                            uint32_t *__restrict__ vals, uint32_t &count) {
+                                            uint32_t *__restrict__ vals, uint32_t &count, const bool pack_masks = false) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	if (active) {
@@ -64,18 +107,18 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 	}
 	const int w = active ? (x1 - x0) : 0, h = active ? (y1 - y0) : 0;
 	const bool coop = w * h > kCoopArea;
-	const float det = cp.a * cp.c - cp.b * cp.b;
+	const EllipseAux ea = ellipse_aux(cp);
 	count = 0;
 	if (active && !coop) {
 		uint32_t off = offset;
 		for (int ty = y0; ty < y1; ty++) {
 			if (band.step != 1 && !band_owns(band, ty)) continue;
 			int xb, xe;
-			row_span(cp, det, ty, x0, x1, xb, xe);
+			row_span(cp, ea, ty, x0, x1, xb, xe);
 			if (EMIT) {
 				for (int tx = xb; tx < xe; tx++) {
 					keys[off] = (uint32_t)(ty * gx + tx);
-					vals[off] = gauss_idx;
+					vals[off] = pack_masks ? (gauss_idx | (warp_mask(cp, ea, tx, ty) << 24)) : gauss_idx;
 					off++;
 				}
 			} else {
@@ -92,7 +135,7 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 		c2.mx = __shfl_sync(full, cp.mx, src); c2.my = __shfl_sync(full, cp.my, src);
 		c2.a = __shfl_sync(full, cp.a, src); c2.b = __shfl_sync(full, cp.b, src);
 		c2.c = __shfl_sync(full, cp.c, src); c2.qmax = __shfl_sync(full, cp.qmax, src);
-		const float det2 = c2.a * c2.c - c2.b * c2.b;
+		const EllipseAux ea2 = ellipse_aux(c2);
 		const int sx0 = __shfl_sync(full, x0, src), sx1 = __shfl_sync(full, x1, src);
 		const int sy0 = __shfl_sync(full, y0, src), sy1 = __shfl_sync(full, y1, src);
 		const uint32_t sidx = __shfl_sync(full, gauss_idx, src);
@@ -101,7 +144,7 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 		for (int r0 = sy0; r0 < sy1; r0 += 32) {  // 32 rows at a time: one row span per lane
 			const int ty = r0 + lane;
 			int xb = 0, xe = 0;
-			if (ty < sy1 && band_owns(band, ty)) row_span(c2, det2, ty, sx0, sx1, xb, xe);
+			if (ty < sy1 && band_owns(band, ty)) row_span(c2, ea2, ty, sx0, sx1, xb, xe);
 			const uint32_t n = (uint32_t)(xe - xb);
 			uint32_t incl = n;  // inclusive warp scan of the per-row counts
 #pragma unroll
@@ -117,7 +160,7 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 					const uint32_t tile0 = (uint32_t)((r0 + r) * gx);
 					for (int tx = rxb + lane; tx < rxe; tx += 32) {
 						keys[rbase + (uint32_t)(tx - rxb)] = tile0 + (uint32_t)tx;
-						vals[rbase + (uint32_t)(tx - rxb)] = sidx;
+						vals[rbase + (uint32_t)(tx - rxb)] = pack_masks ? (sidx | (warp_mask(c2, ea2, tx, r0 + r) << 24)) : sidx;
 					}
 				}
 			}

@@ -42,9 +42,10 @@ def test_oracle_matches_reference_golden(path):
     for k in ("color", "depth", "alpha", "semantic"):
         if k in ref and ref[k].size:
             d = np.abs(res[k].astype(np.float64) - ref[k])
+            scale = max(1.0, float(np.abs(ref[k]).max())) if k == "depth" else 1.0  # depth is un-normalised metres
             # hard thresholds (alpha < 1/255, T < 1e-4) may flip on isolated pixels: plain C vs FMA-contracted GPU code
-            assert (d > 1e-4).sum() <= max(3, npx // 2000), (k, int((d > 1e-4).sum()), float(d.max()))
-            assert np.median(d) < 1e-6
+            assert (d > 1e-4 * scale).sum() <= max(3, npx // 2000), (k, int((d > 1e-4 * scale).sum()), float(d.max()))
+            assert np.median(d) < 1e-6 * scale
     for k, v in ref.items():
         if k.startswith("g_") and res.get(k) is not None and v.size:
             assert util.rel_err(res[k], v) < 3e-3, (k, util.rel_err(res[k], v))

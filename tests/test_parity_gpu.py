@@ -184,10 +184,12 @@ def test_geometry_bitwise_vs_reference():
                                                            None, mst, None)
     torch.cuda.synchronize()
     rec = fst.geom[:P * 48].cpu().numpy().view(np.float32).reshape(P, 12)
-    vis = g["radii"] > 0
-    assert (rad.cpu().numpy() == g["radii"]).all()
+    ref_radii = radii.cpu().numpy()  # (GeometryState.internal_radii is unused when the caller passes a radii tensor)
+    vis = ref_radii > 0
+    assert (rad.cpu().numpy() == ref_radii).all()
     assert vis.sum() > 50_000
-    assert (rec[vis, 6].view(np.uint32) == g["depth"][vis].view(np.uint32)).all(), "view depth must be bit-equal (it is the sort key)"
+    # record layout: q0 = (px, py, conic.xx, conic.xy), q1 = (conic.yy, opacity, power_min, depth), q2 = (r, g, b, clamp bits)
+    assert (rec[vis, 7].view(np.uint32) == g["depth"][vis].view(np.uint32)).all(), "view depth must be bit-equal (it is the sort key)"
 
     def ulps(a, b):
         a = a.astype(np.float32).view(np.int32).astype(np.int64); b = b.astype(np.float32).view(np.int32).astype(np.int64)
@@ -196,9 +198,9 @@ def test_geometry_bitwise_vs_reference():
     assert ulps(rec[vis, 0:2], g["xy"][vis]).max() == 0, "pixel positions"
     assert ulps(rec[vis][:, [2, 3, 4]], g["conic_opacity"][vis, :3]).max() <= 2, "conic"
     assert (rec[vis, 5] == g["conic_opacity"][vis, 3]).all(), "opacity"
-    mine_rgb = np.stack([rec[vis, 7], rec[vis, 8], rec[vis, 9]], 1)
+    mine_rgb = np.stack([rec[vis, 8], rec[vis, 9], rec[vis, 10]], 1)
     assert ulps(mine_rgb, g["rgb"][vis]).max() <= 4, "SH colour"
-    clamp = rec[vis, 10].view(np.uint32)
+    clamp = rec[vis, 11].view(np.uint32)
     assert (((clamp[:, None] >> np.arange(3)) & 1) == g["clamped"][vis]).all()
     # exact tile culling only ever REMOVES instances, and never changes the image
     assert fst.num_instances <= n_ref
