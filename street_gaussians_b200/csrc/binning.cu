@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 		}
 	}
 	uint32_t count;
-	visit_tiles<true>(active, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count, f.P < (1 << 24));
+	visit_tiles<true>(active, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count);
 }
 
 // One thread per sorted instance: a tile's range starts / ends where the tile id changes

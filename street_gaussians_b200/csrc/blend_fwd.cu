@@ -3,12 +3,16 @@
 // Replaces the reference's renderCUDA<3> (DGR/cuda_rasterizer/forward.cu:340-467).  Same per-(pixel, splat) arithmetic
 // (expression shapes kept so `power`, `alpha` and the three hard thresholds flip on exactly the same pairs), different
 // machinery:
-//   * one CTA per OWNED tile (tile-row band), 8 warps, each warp owns a compact 8x4 pixel block (the reference gives a
-//     warp two 16x1 rows) — a small splat then touches fewer warps, which is what the warp-uniform skips key on;
+//   * one CTA per OWNED tile (tile-row band), 8 warps, each warp owns a compact 8x4 pixel block;
 //   * the tile's splat list is staged through shared memory from the packed 48-B GaussRec (3 x 16-B gathers per
 //     instance instead of id + float2 + float4 + per-contribution global re-gathers of colour and depth);
 //   * double-buffered staging with register prefetch: the gathers of batch k+1 are in flight while batch k is blended,
 //     one __syncthreads_count per batch (it doubles as the "whole tile saturated" vote);
+//   * the kernel is ISSUE-bound (ncu: 91% issue-active, <2% DRAM — profiles/), so the inner loop is written for
+//     instruction count: one running 32-bit shared address, three LDS.128 with immediate offsets per splat
+//     (explicit ld.shared — indexing the arrays through C++ made nvcc rebuild a cluster-window address with
+//     S2R/LEA every iteration, 12 of 76 instructions), and a conservative `power` bound from the record that skips
+//     expf for pairs that cannot reach alpha >= 1/255;
 //   * semantics are accumulated in registers and written once (the reference does a global read-modify-write per
 //     contribution, forward.cu:442-444).
 #include "sgr_common.cuh"
@@ -16,6 +20,16 @@
 namespace sgr {
 
 constexpr int kFwdBatch = 256;
+constexpr uint32_t kRecBytes = 48;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 template <int SCH>
 __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
@@ -24,10 +38,8 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
                                                         uint32_t *__restrict__ tile_max_contrib, float *__restrict__ out_color,
                                                         float *__restrict__ out_depth, float *__restrict__ out_alpha,
                                                         float *__restrict__ out_sem, const int sem_ch0, const int sem_only) {
-	__shared__ float4 s_q0[2][kFwdBatch];
-	__shared__ float4 s_q1[2][kFwdBatch];
-	__shared__ float4 s_q2[2][kFwdBatch];
-	__shared__ uint32_t s_id[2][kFwdBatch];  // warp mask << 24 | Gaussian index
+	__shared__ __align__(16) unsigned char s_rec[2][kFwdBatch * kRecBytes];  // 2 x 12 KB: GaussRec per list slot
+	__shared__ uint32_t s_id[SCH > 0 ? 2 : 1][SCH > 0 ? kFwdBatch : 1];
 	__shared__ uint32_t s_max;
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -40,16 +52,13 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 	const size_t pix_id = (size_t)f.W * py + px;
 	const float2 pixf = make_float2((float)px, (float)py);
 
-	// point-list values carry the 8-bit warp mask above the 24-bit index when P < 2^24 (tile_visit.cuh)
-	const bool use_mask = f.P < (1 << 24);
-	const uint32_t idx_mask = use_mask ? kIdxMask : 0xffffffffu;
-	const uint32_t my_bit = use_mask ? (1u << (24 + warp)) : 0u;
-
 	const uint2 range = ranges[tile];
 	const int n = (int)(range.y - range.x);
 	const int nb = (n + kFwdBatch - 1) / kFwdBatch;
 	if (tid == 0) s_max = 0;
 	__syncthreads();
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_rec[0][0]);
+	constexpr uint32_t kBufBytes = kFwdBatch * kRecBytes;
 
 	bool done = !inside;
 	float T = 1.0f;
@@ -66,13 +75,14 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 		const int k = b * kFwdBatch + tid;
 		if (k < n) {
 			rid = point_list[range.x + k];
-			const GaussRec *p = rec + (rid & idx_mask);
+			const GaussRec *p = rec + rid;
 			r0 = p->q0; r1 = p->q1; r2 = p->q2;
 		}
 	};
 	auto stash = [&](int buf) {
-		s_q0[buf][tid] = r0; s_q1[buf][tid] = r1; s_q2[buf][tid] = r2;
-		s_id[buf][tid] = rid;
+		const uint32_t a = sbase + (uint32_t)buf * kBufBytes + (uint32_t)tid * kRecBytes;
+		sts128(a, r0); sts128(a + 16, r1); sts128(a + 32, r2);
+		if (SCH > 0) s_id[buf][tid] = rid;
 	};
 	if (nb > 0) { fetch(0); stash(0); }
 
@@ -83,12 +93,12 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 		if (b + 1 < nb) fetch(b + 1);
 		const int buf = b & 1;
 		const int cnt = min(kFwdBatch, n - b * kFwdBatch);
-		const uint32_t pos0 = (uint32_t)(b * kFwdBatch);
-		for (int j = 0; !done && j < cnt; j++) {
-			const uint32_t v = s_id[buf][j];
-			if (my_bit != 0u && (v & my_bit) == 0u) continue;  // warp-uniform: this 8x4 block cannot receive anything
-			const float4 q0 = s_q0[buf][j];
-			const float4 q1 = s_q1[buf][j];
+		const uint32_t a0 = sbase + (uint32_t)buf * kBufBytes;
+		const uint32_t a_end = a0 + (uint32_t)cnt * kRecBytes;
+		uint32_t a_last = 0xffffffffu;
+		for (uint32_t a = a0; !done && a < a_end; a += kRecBytes) {
+			const float4 q0 = lds128(a);       // pix.x, pix.y, conic.xx, conic.xy
+			const float4 q1 = lds128(a + 16);  // conic.yy, opacity, power_min, depth
 			const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
 			const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
 			if (power > 0.0f) continue;
@@ -100,12 +110,13 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 				done = true;
 				continue;
 			}
-			const float4 q2 = s_q2[buf][j];
+			const float4 q2 = lds128(a + 32);  // r, g, b, clamp bits
 			C0 += q2.x * alpha * T;
 			C1 += q2.y * alpha * T;
 			C2 += q2.z * alpha * T;
 			if (SCH > 0) {
-				const float *sp = semantics + (size_t)(v & idx_mask) * f.S + sem_ch0;
+				const uint32_t j = (a - a0) / kRecBytes;
+				const float *sp = semantics + (size_t)s_id[buf][j] * f.S + sem_ch0;
 #pragma unroll
 				for (int c = 0; c < SCH; c++)
 					if (c < nsem) sem[c] += __ldg(sp + c) * alpha * T;
@@ -113,8 +124,9 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const FrameDev f, const 
 			weight += alpha * T;
 			Dacc += q1.w * alpha * T;
 			T = test_T;
-			last_contributor = pos0 + (uint32_t)j + 1u;
+			a_last = a;
 		}
+		if (a_last != 0xffffffffu) last_contributor = (uint32_t)(b * kFwdBatch) + (a_last - a0) / kRecBytes + 1u;
 		if (b + 1 < nb) stash((b + 1) & 1);
 	}
 

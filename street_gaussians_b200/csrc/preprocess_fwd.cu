@@ -105,7 +105,7 @@ __device__ __forceinline__ Projected project_gaussian(const FrameDev &f, int idx
 }
 
 // SH (degree <= 3) -> RGB with +0.5 and clamp-at-zero flags (reference forward.cu:20-71).  sh points at this
-// Gaussian's [M,3] coefficient row (staged in shared memory by the caller, or global memory).
+// Gaussian's [M,3] coefficient row in global memory.
 __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float3 campos, const float *__restrict__ sh, int M,
                                             uint32_t &clamp_bits) {
 	float3 d = make_float3(p.x - campos.x, p.y - campos.y, p.z - campos.z);
@@ -113,9 +113,22 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float
 	const float x = d.x / len, y = d.y / len, z = d.z / len;
 	float c[48];
 	const int n = min(M, (deg + 1) * (deg + 1)) * 3;
+	// Each thread walks its own 12*M-byte row with 16-B loads; the two halves of every 32-B sector are consumed by
+	// consecutive loads of the same thread, so L1 absorbs the stride.  (Staging the rows through shared memory, as
+	// preprocess_bwd does for its read+write pair, was measured SLOWER here: 264 vs 168 us on config C — profiles/.)
+	if (((M * 3) & 3) == 0) {
+		const float4 *s4 = reinterpret_cast<const float4 *>(sh);
 #pragma unroll
-	for (int k = 0; k < 48; k++)
-		if (k < n) c[k] = sh[k];
+		for (int k = 0; k < 12; k++)
+			if (4 * k < n) {
+				const float4 v = __ldg(s4 + k);
+				c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+			}
+	} else {
+#pragma unroll
+		for (int k = 0; k < 48; k++)
+			if (k < n) c[k] = __ldg(sh + k);
+	}
 	float res[3];
 #pragma unroll
 	for (int ch = 0; ch < 3; ch++) {
@@ -143,8 +156,6 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float
 	return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
 }
 
-constexpr int kShRowF = 49;  // padded smem row (floats) for up to 16 x 3 SH coefficients
-
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, const float *__restrict__ means3D,
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,
                                                              const float *__restrict__ opacities, const float *__restrict__ scales,
@@ -152,9 +163,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
                                                              int32_t *__restrict__ radii, GaussRec *__restrict__ rec,
                                                              uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ depth_key,
                                                              uint32_t *__restrict__ iota) {
-	extern __shared__ float s_sh[];  // [8 warps][32][kShRowF] SH staging (only when shs != nullptr and M <= 16)
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const bool in_range = idx < f.P;
 	Projected pr;
 	pr.ok = false;
@@ -165,45 +174,13 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
 		pr = project_gaussian(f, idx, p, scales, rotations, cov3D_precomp);
 	}
-	const bool staged = shs != nullptr && f.M <= 16;
-	if (staged) {
-		// The 32 Gaussians of a warp own one contiguous 32 x M x 3 block of `shs`: move the rows of the surviving
-		// Gaussians with coalesced 16-B loads (only the coefficients of the active degree), rows padded to 49 floats
-		// so the per-thread row reads below are bank-conflict free.
-		const unsigned ok_mask = __ballot_sync(0xffffffffu, pr.ok);
-		const int nsh = f.M * 3, n = min(f.M, (f.D + 1) * (f.D + 1)) * 3;
-		const size_t g0 = (size_t)(blockIdx.x * blockDim.x + warp * 32);
-		float *wbase = s_sh + (size_t)warp * 32 * kShRowF;
-		if (ok_mask) {
-			if (((nsh | n) & 3) == 0) {
-				const float4 *src = reinterpret_cast<const float4 *>(shs + g0 * nsh);
-				const int n4 = n / 4, nsh4 = nsh / 4;
-				for (int e = lane; e < 32 * n4; e += 32) {
-					const int row = e / n4, col4 = e - row * n4;
-					if ((ok_mask >> row) & 1u) {
-						const float4 v = __ldg(src + row * nsh4 + col4);
-						float *d = wbase + row * kShRowF + 4 * col4;
-						d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-					}
-				}
-			} else {
-				const float *src = shs + g0 * nsh;
-				for (int e = lane; e < 32 * n; e += 32) {
-					const int row = e / n, col = e - row * n;
-					if ((ok_mask >> row) & 1u) wbase[row * kShRowF + col] = __ldg(src + (size_t)row * nsh + col);
-				}
-			}
-		}
-		__syncwarp();
-	}
 	if (in_range) {
 		if (pr.ok) {
 			float3 rgb;
 			uint32_t clamp_bits = 0;
 			if (colors_precomp == nullptr) {
 				const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
-				const float *row = staged ? (s_sh + ((size_t)warp * 32 + lane) * kShRowF) : (shs + (size_t)idx * f.M * 3);
-				rgb = sh_to_rgb(f.D, p, campos, row, f.M, clamp_bits);
+				rgb = sh_to_rgb(f.D, p, campos, shs + (size_t)idx * f.M * 3, f.M, clamp_bits);
 			} else {
 				rgb = make_float3(colors_precomp[3 * (size_t)idx], colors_precomp[3 * (size_t)idx + 1], colors_precomp[3 * (size_t)idx + 2]);
 			}
@@ -254,14 +231,7 @@ cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const
                                   const float *opacities, const float *scales, const float *rotations,
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
-	const size_t smem = (shs != nullptr && f.M <= 16) ? (size_t)8 * 32 * kShRowF * sizeof(float) : 0;  // 50,176 B
-	static bool configured = false;
-	if (smem && !configured) {
-		cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return e;
-		configured = true;
-	}
-	preprocess_fwd_kernel<<<(f.P + 255) / 256, 256, smem, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
+	preprocess_fwd_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
 	                                                            cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
 	return cudaGetLastError();
 }

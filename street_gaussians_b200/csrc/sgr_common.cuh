@@ -131,8 +131,6 @@ ImgView carve_img(void *base, int W, int H);
 BinView carve_bin(void *base, int64_t R);
 
 // kernel launchers (host) — one per translation unit
-constexpr uint32_t kIdxMask = 0x00ffffffu;  // point-list value = warp mask << 24 | Gaussian index (when P < 2^24)
-
 struct FrameDev {  // SgrFrame + derived values, passed by value to kernels
 	int P, D, M, S, W, H, gx, gy;
 	float tanx, tany, fx, fy, mod;

@@ -9,9 +9,9 @@
 // that interval, so this is exactly the per-tile test, at O(rows) instead of O(rows x cols) cost, with the same
 // conservative slack (a tile that is kept needlessly only costs time; a dropped tile provably receives nothing).
 //
-// At emission the value carries, above the 24-bit Gaussian index, an 8-bit mask of the tile's eight 8x4-pixel blocks that
-// can receive a contribution (same closed form on 4-pixel strips); the blend kernels map one warp to each block and
-// skip a splat outright when their bit is clear.  (Only when P < 2^24; otherwise the value is the plain index.)
+// (Tried and measured on B200, then removed: an extra 8-bit mask per instance of the tile's eight 8x4-pixel blocks so that
+// the blend warps could skip splats that miss their block.  On the BASELINE config-C frame pixels saturate on large near
+// splats, only 4% of warp-iterations were skipped, and the per-tile mask math made this kernel 5x slower — profiles/.)
 //
 // Small rectangles are walked by the owning thread; rectangles above kCoopArea tiles are walked by the whole warp so one
 // screen-filling splat cannot serialise 10^4 iterations on one thread (the reference's duplicateWithKeys does,
@@ -74,30 +74,10 @@ __device__ __forceinline__ void row_span(const CullParams cp, const EllipseAux e
 	if (xe < xb) xe = xb;
 }
 
-// Which of the tile's eight 8x4-pixel blocks (= the eight warps of the blend kernels: bit 2*sr + half, sr = pixel-row
-// quarter, half = left/right 8 columns) can receive a contribution.  Same closed form on 4-pixel-high strips.
-__device__ __forceinline__ uint32_t warp_mask(const CullParams cp, const EllipseAux ea, int tx, int ty) {
-	if (!(cp.qmax < __int_as_float(0x7f800000))) return 0xffu;
-	const float ux0 = (float)(tx * SGR_TILE) - cp.mx;  // relative x of the tile's first pixel column
-	uint32_t m = 0;
-#pragma unroll
-	for (int sr = 0; sr < 4; sr++) {
-		const float uy0 = (float)(ty * SGR_TILE + 4 * sr) - cp.my;
-		float xmin, xmax;
-		if (!strip_xrange(cp, ea.det, ea.xext, ea.yhi, uy0, uy0 + 3.f, xmin, xmax)) continue;
-		xmin -= 0.05f;
-		xmax += 0.05f;
-		const bool left = (ux0 <= xmax) && (ux0 + 7.f >= xmin);
-		const bool right = (ux0 + 8.f <= xmax) && (ux0 + 15.f >= xmin);
-		m |= (left ? 1u : 0u) << (2 * sr) | (right ? 1u : 0u) << (2 * sr + 1);
-	}
-	return m;
-}
-
 template <bool EMIT>
 __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1, int y1, const CullParams cp, const Band band,
                                             int gx, uint32_t gauss_idx, uint32_t offset, uint32_t *__restrict__ keys,
-                                            uint32_t *__restrict__ vals, uint32_t &count, const bool pack_masks = false) {
+                                            uint32_t *__restrict__ vals, uint32_t &count) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	if (active) {
@@ -118,7 +98,7 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 			if (EMIT) {
 				for (int tx = xb; tx < xe; tx++) {
 					keys[off] = (uint32_t)(ty * gx + tx);
-					vals[off] = pack_masks ? (gauss_idx | (warp_mask(cp, ea, tx, ty) << 24)) : gauss_idx;
+					vals[off] = gauss_idx;
 					off++;
 				}
 			} else {
@@ -160,7 +140,7 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 					const uint32_t tile0 = (uint32_t)((r0 + r) * gx);
 					for (int tx = rxb + lane; tx < rxe; tx += 32) {
 						keys[rbase + (uint32_t)(tx - rxb)] = tile0 + (uint32_t)tx;
-						vals[rbase + (uint32_t)(tx - rxb)] = pack_masks ? (sidx | (warp_mask(c2, ea2, tx, r0 + r) << 24)) : sidx;
+						vals[rbase + (uint32_t)(tx - rxb)] = sidx;
 					}
 				}
 			}
