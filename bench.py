@@ -23,9 +23,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -54,44 +52,60 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md 'clocks' line)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle-reason sampler running DURING the timed region (B200_PROFILING.md 'clocks' line).
 
-    def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    In-process NVML polling from a background thread (pynvml).  An external `nvidia-smi -lms 100` loop was measured to
+    perturb this host-synchronising workload badly (4.0 ms/step with it vs 2.2 ms without: every query takes driver
+    locks that the mid-forward cudaStreamSynchronize then waits on); if NVML is unavailable the record says so."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
+        import threading
+        self.samples, self.marks, self._stop = [], [None, None], threading.Event()
+        self.h = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.h = None
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while not self._stop.is_set():
+            if self.h is not None:
+                try:
+                    sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    try:
+                        rs = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        rs = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append((time.perf_counter(), sm, rs))
+                except Exception:
+                    pass
+            self._stop.wait(self.period)
+
+    def mark(self, which: int):
+        self.marks[which] = time.perf_counter()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.strip().lower().startswith("active"):
+        self._stop.set()
+        self.t.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml" if self.h is not None else "unavailable"}
+        t0, t1 = self.marks
+        sel = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)] or self.samples[-3:]
+        if sel:
+            reasons = set()
+            for _, _, rs in sel:
+                for nm, bit in self.REASONS.items():
+                    if rs & bit:
                         reasons.add(nm)
-            except Exception:
-                pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median([s[1] for s in sel])), sm_max_mhz=self.sm_max, reasons=sorted(reasons), samples=len(sel))
         return out
 
 
@@ -213,11 +227,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark(0)
     e0.record()
     for _ in range(args.steps):
         color, radii = step()
@@ -314,6 +330,8 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    if sampler:
+        sampler.mark(1)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:

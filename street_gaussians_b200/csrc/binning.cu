@@ -52,28 +52,39 @@ cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st) {
 	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, f.P, st);
 }
 
+constexpr uint32_t kEmitStage = 512;  // instances staged per warp (2 x 2 KB of shared memory per warp)
+
 // thread t handles the t-th Gaussian in depth order
 __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const GaussRec *__restrict__ rec, const int32_t *__restrict__ radii,
-                                                        const uint32_t *__restrict__ tiles_touched, const uint32_t *__restrict__ perm,
+                                                        const uint32_t *__restrict__ /*tiles_touched*/, const uint32_t *__restrict__ perm,
                                                         const uint32_t *__restrict__ offsets, uint32_t *__restrict__ keys,
                                                         uint32_t *__restrict__ vals) {
+	__shared__ uint32_t s_keys[8][kEmitStage], s_vals[8][kEmitStage];
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int warp = threadIdx.x >> 5;
 	bool active = false;
 	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
 	CullParams cp = {};
-	uint32_t off = 0, gidx = 0;
+	uint32_t gidx = 0;
+	// [off, end) = this Gaussian's output range (offsets = inclusive scan in depth order); lanes past P get an empty range
+	const int tc = min(t, f.P - 1);
+	uint32_t end = offsets[tc];
+	uint32_t off = tc == 0 ? 0u : offsets[tc - 1];
+	if (t >= f.P) off = end;
 	if (t < f.P) {
 		gidx = perm[t];
-		if (tiles_touched[gidx] > 0) {
+		if (end > off) {
 			const float4 q0 = rec[gidx].q0, q1 = rec[gidx].q1;
 			tile_rect(q0.x, q0.y, radii[gidx], f.gx, f.gy, x0, y0, x1, y1);
 			cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-			off = t == 0 ? 0u : offsets[t - 1];
 			active = true;
 		}
 	}
+	const uint32_t warp_first = __shfl_sync(0xffffffffu, off, 0);
+	const uint32_t warp_total = __shfl_sync(0xffffffffu, end, 31) - warp_first;
 	uint32_t count;
-	visit_tiles<true>(active, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count);
+	visit_tiles<true>(active, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count, s_keys[warp], s_vals[warp], kEmitStage,
+	                  warp_first, warp_total);
 }
 
 // One thread per sorted instance: a tile's range starts / ends where the tile id changes

@@ -77,7 +77,9 @@ __device__ __forceinline__ void row_span(const CullParams cp, const EllipseAux e
 template <bool EMIT>
 __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1, int y1, const CullParams cp, const Band band,
                                             int gx, uint32_t gauss_idx, uint32_t offset, uint32_t *__restrict__ keys,
-                                            uint32_t *__restrict__ vals, uint32_t &count) {
+                                            uint32_t *__restrict__ vals, uint32_t &count, uint32_t *stage_keys = nullptr,
+                                            uint32_t *stage_vals = nullptr, uint32_t stage_cap = 0, uint32_t warp_first = 0,
+                                            uint32_t warp_total = 0) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	if (active) {
@@ -89,6 +91,12 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 	const bool coop = w * h > kCoopArea;
 	const EllipseAux ea = ellipse_aux(cp);
 	count = 0;
+	unsigned todo = __ballot_sync(full, coop);
+	// Emission of a warp's 32 (depth-consecutive) Gaussians covers ONE contiguous output range.  When it fits the
+	// per-warp shared-memory stage (and no lane needs the cooperative path) the lanes scatter into shared memory and the
+	// warp then copies the range out with fully coalesced stores; per-thread global scatter (32 sectors per store
+	// instruction) is the fallback.
+	const bool staged = EMIT && stage_keys != nullptr && todo == 0u && warp_total <= stage_cap;
 	if (active && !coop) {
 		uint32_t off = offset;
 		for (int ty = y0; ty < y1; ty++) {
@@ -96,10 +104,18 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 			int xb, xe;
 			row_span(cp, ea, ty, x0, x1, xb, xe);
 			if (EMIT) {
-				for (int tx = xb; tx < xe; tx++) {
-					keys[off] = (uint32_t)(ty * gx + tx);
-					vals[off] = gauss_idx;
-					off++;
+				if (staged) {
+					for (int tx = xb; tx < xe; tx++) {
+						stage_keys[off - warp_first] = (uint32_t)(ty * gx + tx);
+						stage_vals[off - warp_first] = gauss_idx;
+						off++;
+					}
+				} else {
+					for (int tx = xb; tx < xe; tx++) {
+						keys[off] = (uint32_t)(ty * gx + tx);
+						vals[off] = gauss_idx;
+						off++;
+					}
 				}
 			} else {
 				off += (uint32_t)(xe - xb);
@@ -107,7 +123,13 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 		}
 		count = off - offset;
 	}
-	unsigned todo = __ballot_sync(full, coop);
+	if (staged) {
+		__syncwarp();
+		for (uint32_t i = lane; i < warp_total; i += 32) {
+			keys[warp_first + i] = stage_keys[i];
+			vals[warp_first + i] = stage_vals[i];
+		}
+	}
 	while (todo) {
 		const int src = __ffs(todo) - 1;
 		todo &= todo - 1;

@@ -199,7 +199,10 @@ def test_geometry_bitwise_vs_reference():
     assert ulps(rec[vis][:, [2, 3, 4]], g["conic_opacity"][vis, :3]).max() <= 2, "conic"
     assert (rec[vis, 5] == g["conic_opacity"][vis, 3]).all(), "opacity"
     mine_rgb = np.stack([rec[vis, 8], rec[vis, 9], rec[vis, 10]], 1)
-    assert ulps(mine_rgb, g["rgb"][vis]).max() <= 4, "SH colour"
+    # SH colour is a 16-term signed sum: near a zero crossing a 1e-7 absolute difference is thousands of ulps, so bound
+    # the absolute error and require ulp-level agreement for (almost) all entries
+    assert np.abs(mine_rgb - g["rgb"][vis]).max() <= 1e-6, "SH colour (abs)"
+    assert (ulps(mine_rgb, g["rgb"][vis]) <= 4).mean() > 0.999, "SH colour (ulps)"
     clamp = rec[vis, 11].view(np.uint32)
     assert (((clamp[:, None] >> np.arange(3)) & 1) == g["clamped"][vis]).all()
     # exact tile culling only ever REMOVES instances, and never changes the image
