@@ -121,7 +121,7 @@ struct CullParams {
 __device__ __forceinline__ CullParams make_cull(float mx, float my, float a, float b, float c, float opacity) {
 	CullParams cp{mx, my, a, b, c, __int_as_float(0x7f800000)};
 	const bool pd = (a > 0.f) && (c > 0.f) && (a * c - b * b > 0.f);
-	const float tau = logf(255.0f * opacity);  // NaN for negative / NaN opacity -> comparison below fails -> keep
+	const float tau = __logf(255.0f * opacity);  // (approximate log: the slack below dwarfs its error) NaN for negative / NaN opacity -> keep
 	if (pd && tau == tau) cp.qmax = 2.0f * tau + (0.02f + 1e-3f * fabsf(tau));
 	return cp;
 }

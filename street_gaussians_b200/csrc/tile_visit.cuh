@@ -23,36 +23,42 @@ namespace sgr {
 
 constexpr int kCoopArea = 64;
 
+// Approximate (MUFU-based, ~2 ulp) division / square root: this file only decides which tiles are KEPT, with slack
+// (0.05 px on the interval ends, 0.02 + 1e-3|tau| on qmax) that is orders of magnitude above their error, and count and emit
+// evaluate the identical code, so the IEEE versions (10-15 dependent instructions each) buy nothing here.
+__device__ __forceinline__ float fast_sqrt(float x) { return x * __frsqrt_rn(fmaxf(x, 1e-30f)); }
+__device__ __forceinline__ float fast_div(float x, float y) { return __fdividef(x, y); }
+
 // x-extent [xmin, xmax] (relative to the centre) of {ellipse q <= qmax} ∩ {uy0 <= y <= uy1}; false if empty.
 // Requires a finite qmax and a positive-definite conic (make_cull guarantees both when qmax is finite).
-__device__ __forceinline__ bool strip_xrange(const CullParams cp, const float det, const float xext, const float yhi, float uy0,
-                                             float uy1, float &xmin, float &xmax) {
-	const float yc = fminf(fmaxf(0.f, uy0), uy1);          // strip row closest to the centre
-	if ((det / cp.a) * yc * yc > cp.qmax) return false;    // min_x q(x, yc) = (c - b^2/a) yc^2
-	xmax = xext;
-	xmin = -xext;
-	if (yhi < uy0 || yhi > uy1) {
-		const float y = fminf(fmaxf(yhi, uy0), uy1);
-		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
-		xmax = (-cp.b * y + sqrtf(disc)) / cp.a;
-	}
-	if (-yhi < uy0 || -yhi > uy1) {
-		const float y = fminf(fmaxf(-yhi, uy0), uy1);
-		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
-		xmin = (-cp.b * y - sqrtf(disc)) / cp.a;
-	}
-	return true;
-}
-
 struct EllipseAux {
-	float det, xext, yhi;  // det of the conic; extreme |x| of the ellipse, reached at y = -/+ yhi
+	float det_over_a, inv_a, xext, yhi;  // det/a, 1/a; extreme |x| of the ellipse, reached at y = -/+ yhi
 };
 __device__ __forceinline__ EllipseAux ellipse_aux(const CullParams cp) {
 	EllipseAux e;
-	e.det = cp.a * cp.c - cp.b * cp.b;
-	e.xext = sqrtf(cp.qmax * cp.c / e.det);
-	e.yhi = -cp.b * e.xext / cp.c;
+	const float det = cp.a * cp.c - cp.b * cp.b;
+	e.inv_a = fast_div(1.0f, cp.a);
+	e.det_over_a = det * e.inv_a;
+	e.xext = fast_sqrt(fast_div(cp.qmax * cp.c, det));
+	e.yhi = -cp.b * fast_div(e.xext, cp.c);
 	return e;
+}
+__device__ __forceinline__ bool strip_xrange(const CullParams cp, const EllipseAux ea, float uy0, float uy1, float &xmin, float &xmax) {
+	const float yc = fminf(fmaxf(0.f, uy0), uy1);             // strip row closest to the centre
+	if (ea.det_over_a * yc * yc > cp.qmax + 1e-3f) return false;  // min_x q(x, yc) = (c - b^2/a) yc^2
+	xmax = ea.xext;
+	xmin = -ea.xext;
+	if (ea.yhi < uy0 || ea.yhi > uy1) {
+		const float y = fminf(fmaxf(ea.yhi, uy0), uy1);
+		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
+		xmax = (-cp.b * y + fast_sqrt(disc)) * ea.inv_a;
+	}
+	if (-ea.yhi < uy0 || -ea.yhi > uy1) {
+		const float y = fminf(fmaxf(-ea.yhi, uy0), uy1);
+		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
+		xmin = (-cp.b * y - fast_sqrt(disc)) * ea.inv_a;
+	}
+	return true;
 }
 
 // tile columns [xb, xe) of row `ty` (clipped to [x0, x1)) that can receive a contribution
@@ -62,7 +68,7 @@ __device__ __forceinline__ void row_span(const CullParams cp, const EllipseAux e
 	if (!(cp.qmax < __int_as_float(0x7f800000))) return;  // +inf (non-PD / NaN input): keep the whole rectangle row
 	const float uy0 = (float)(ty * SGR_TILE) - cp.my;
 	float xmin, xmax;
-	if (!strip_xrange(cp, ea.det, ea.xext, ea.yhi, uy0, uy0 + (SGR_TILE - 1), xmin, xmax)) {
+	if (!strip_xrange(cp, ea, uy0, uy0 + (SGR_TILE - 1), xmin, xmax)) {
 		xe = xb;
 		return;
 	}
