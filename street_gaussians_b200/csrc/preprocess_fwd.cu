@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		radii[idx] = pr.radius;
 	}
 	uint32_t count = 0;
-	visit_tiles<false>(pr.ok, pr.x0, pr.y0, pr.x1, pr.y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
+	visit_tiles<false, uint32_t>(pr.ok, pr.x0, pr.y0, pr.x1, pr.y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
 	if (in_range) {
 		tiles_touched[idx] = count;
 		// sort key of the depth pre-sort: Gaussians that emit nothing go to the very end

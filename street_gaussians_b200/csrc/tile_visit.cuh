@@ -80,10 +80,10 @@ __device__ __forceinline__ void row_span(const CullParams cp, const EllipseAux e
 	if (xe < xb) xe = xb;
 }
 
-template <bool EMIT>
+template <bool EMIT, typename KeyT = uint32_t>
 __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1, int y1, const CullParams cp, const Band band,
-                                            int gx, uint32_t gauss_idx, uint32_t offset, uint32_t *__restrict__ keys,
-                                            uint32_t *__restrict__ vals, uint32_t &count, uint32_t *stage_keys = nullptr,
+                                            int gx, uint32_t gauss_idx, uint32_t offset, KeyT *__restrict__ keys,
+                                            uint32_t *__restrict__ vals, uint32_t &count, KeyT *stage_keys = nullptr,
                                             uint32_t *stage_vals = nullptr, uint32_t stage_cap = 0, uint32_t warp_first = 0,
                                             uint32_t warp_total = 0) {
 	const unsigned full = 0xffffffffu;
@@ -112,13 +112,13 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 			if (EMIT) {
 				if (staged) {
 					for (int tx = xb; tx < xe; tx++) {
-						stage_keys[off - warp_first] = (uint32_t)(ty * gx + tx);
+						stage_keys[off - warp_first] = (KeyT)(ty * gx + tx);
 						stage_vals[off - warp_first] = gauss_idx;
 						off++;
 					}
 				} else {
 					for (int tx = xb; tx < xe; tx++) {
-						keys[off] = (uint32_t)(ty * gx + tx);
+						keys[off] = (KeyT)(ty * gx + tx);
 						vals[off] = gauss_idx;
 						off++;
 					}
@@ -167,7 +167,7 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 					const uint32_t rbase = base + __shfl_sync(full, incl - n, r);
 					const uint32_t tile0 = (uint32_t)((r0 + r) * gx);
 					for (int tx = rxb + lane; tx < rxe; tx += 32) {
-						keys[rbase + (uint32_t)(tx - rxb)] = tile0 + (uint32_t)tx;
+						keys[rbase + (uint32_t)(tx - rxb)] = (KeyT)(tile0 + (uint32_t)tx);
 						vals[rbase + (uint32_t)(tx - rxb)] = sidx;
 					}
 				}

@@ -274,7 +274,7 @@ def test_edge_cases():
     color, radii, depth, alpha, sem = rast(means3D=m, means2D=None, opacities=torch.rand(P, 1, device=dev), shs=sh,
                                            scales=torch.rand(P, 3, device=dev), rotations=torch.rand(P, 4, device=dev))
     assert (radii == 0).all() and float(alpha.max()) == 0.0
-    np.testing.assert_allclose(color[:, 0, 0].cpu().numpy(), [0.1, 0.2, 0.3], rtol=1e-6)
+    np.testing.assert_allclose(color[:, 0, 0].detach().cpu().numpy(), [0.1, 0.2, 0.3], rtol=1e-6)
     color.sum().backward()
     assert float(m.grad.abs().max()) == 0.0 and float(sh.grad.abs().max()) == 0.0
     assert sem.shape == (0, 60, 100)
