@@ -61,17 +61,12 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const GaussRec *__restrict__ rec, const int32_t *__restrict__ radii,
                                                         const uint32_t *__restrict__ /*tiles_touched*/, const uint32_t *__restrict__ perm,
                                                         const uint32_t *__restrict__ offsets, KeyT *__restrict__ keys,
-                                                        uint32_t *__restrict__ vals, const uint32_t chunk_stride) {
+                                                        uint32_t *__restrict__ vals, uint32_t *__restrict__ big_list,
+                                                        uint32_t *__restrict__ big_count) {
 	__shared__ KeyT s_keys[8][kEmitStage];
 	__shared__ uint32_t s_vals[8][kEmitStage];
 	const int warp = threadIdx.x >> 5;
-	// Depth order puts the nearest (= largest on screen, most tiles) Gaussians at the front of the list.  Handing CTAs
-	// consecutive 256-Gaussian slices made the first CTAs many times heavier than the rest (ncu: busiest SM 492k cycles,
-	// mean 234k).  Each warp still takes 32 depth-consecutive Gaussians (one contiguous output range), but the 32-chunks
-	// are dealt to warps through a fixed permutation (multiplication by a stride coprime to the chunk count).
-	const uint32_t nchunks = gridDim.x * 8u;
-	const uint32_t chunk = (uint32_t)(((unsigned long long)(blockIdx.x * 8u + (uint32_t)warp) * chunk_stride) % nchunks);
-	const int t = (int)(chunk * 32u + (threadIdx.x & 31u));
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	bool active = false;
 	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
 	CullParams cp = {};
@@ -94,7 +89,30 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 	const uint32_t warp_total = __shfl_sync(0xffffffffu, end, 31) - warp_first;
 	uint32_t count;
 	visit_tiles<true, KeyT>(active, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count, s_keys[warp], s_vals[warp], kEmitStage,
-	                  warp_first, warp_total);
+	                  warp_first, warp_total, big_list, big_count, (uint32_t)t);
+}
+
+// One warp per deferred (large-rectangle) Gaussian, grid-strided over the device-side list: no host round trip for the count.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) emit_big_kernel(const FrameDev f, const GaussRec *__restrict__ rec, const int32_t *__restrict__ radii,
+                                                      const uint32_t *__restrict__ perm, const uint32_t *__restrict__ offsets,
+                                                      KeyT *__restrict__ keys, uint32_t *__restrict__ vals,
+                                                      const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count) {
+	const uint32_t n = *big_count;
+	const uint32_t nwarps = gridDim.x * 8u;
+	const int lane = threadIdx.x & 31;
+	for (uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5); i < n; i += nwarps) {
+		const uint32_t t = big_list[i];
+		const uint32_t gidx = perm[t];
+		const float4 q0 = rec[gidx].q0, q1 = rec[gidx].q1;
+		int x0, y0, x1, y1;
+		tile_rect(q0.x, q0.y, radii[gidx], f.gx, f.gy, x0, y0, x1, y1);
+		const CullParams cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+		const uint32_t off = t == 0 ? 0u : offsets[t - 1];
+		// lane 0 carries the Gaussian through the cooperative path of visit_tiles (all other lanes inactive)
+		uint32_t count;
+		visit_tiles<true, KeyT>(lane == 0, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count);
+	}
 }
 
 // One thread per sorted instance: a tile's range starts / ends where the tile id changes
@@ -128,20 +146,20 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 	if (e != cudaSuccess) return e;
 	if (R == 0 || f.P == 0) return cudaSuccess;
 	size_t bytes = b.sort_temp_bytes;
-	const unsigned nblk = (unsigned)((f.P + 255) / 256), nchunks = nblk * 8u;
-	unsigned stride = (unsigned)(nchunks * 0.6180339887) | 1u;  // golden-ratio stride, made coprime to the chunk count
-	auto gcd = [](unsigned a, unsigned b) { while (b) { unsigned t = a % b; a = b; b = t; } return a; };
-	while (stride > 1 && gcd(stride, nchunks) != 1) stride += 2;
-	if (stride >= nchunks || nchunks <= 8) stride = 1;
+	const unsigned nblk = (unsigned)((f.P + 255) / 256);
+	const unsigned nbig_blk = 148 * 4;  // persistent-style grid for the deferred large rectangles
+	if ((e = cudaMemsetAsync(g.big_count, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
 	if (ntile <= 65536) {  // 16-bit tile ids (the key arrays are allocated for 32-bit ids either way)
 		uint16_t *kin = reinterpret_cast<uint16_t *>(b.keys_in), *kout = reinterpret_cast<uint16_t *>(b.keys_out);
-		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, stride);
+		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count);
+		emit_big_kernel<uint16_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, kin, kout, b.vals_in, b.vals_out, R, 0, bits_for(ntile), st);
 		if (e != cudaSuccess) return e;
 		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, kout, img.ranges);
 	} else {
-		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, stride);
+		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count);
+		emit_big_kernel<uint32_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, R, 0, bits_for(ntile), st);
 		if (e != cudaSuccess) return e;

@@ -1,0 +1,267 @@
+// blend_bwd2.cu — two-phase backward blend (the S == 0 fast path; blend_bwd.cu remains the path with feature channels).
+//
+// blend_bwd.cu is issue-bound and spends ~40 % of its instructions turning 32 per-pixel values into one per-splat sum
+// (13 shuffles + 26 selects + 13 adds + the 12 products per (warp, splat)).  This kernel removes the warp reduction:
+//
+//   phase 1 (thread = pixel, back-to-front over a batch of 32 splats): the reference's per-pixel recurrences
+//            (backward.cu:505-614: T, colour/depth/alpha "behind" accumulators, dL/dalpha) produce just TWO numbers per
+//            (pixel, splat) pair,  w = alpha*T  and  q = G*dL/dG,  stored to a [32 splats][256 pixels] shared matrix;
+//   phase 2 (thread = (splat, 32-pixel chunk)): every sum the reference accumulates with atomics is linear in w or q:
+//              colour/depth grads      sum_p w * dL/dpixel_p
+//              moments                 sum_p q * {1, dx, dy, dx^2, dx dy, dy^2}   -> mean2D.xy, conic, opacity (= Sq / o)
+//              |.| statistic           sum_p |q| (|a dx + b dy| W/2 + |c dy + b dx| H/2)
+//            so each thread walks its chunk of the matrix row (bank-rotated, conflict free) accumulating 11 registers,
+//            the 8 chunk-threads of a splat combine with a 3-step butterfly, and 11 global atomics per (tile, splat) leave
+//            the SM — exactly one per component, as in blend_bwd.cu.
+// No per-pair shuffles, selects or shared-memory partial slabs.  Same math as blend_bwd.cu up to summation order.
+#include "sgr_common.cuh"
+
+namespace sgr {
+
+constexpr int kB2 = 32;  // splats per batch
+constexpr uint32_t kRec2 = 48;
+constexpr uint32_t kOffWQ = 0;                            // float2 [kB2][256]
+constexpr uint32_t kOffPix = kB2 * 256 * 8;               // float4 [256]   dL/dpixel rgb, dL/dpixel depth
+constexpr uint32_t kOffPxy = kOffPix + 256 * 16;          // float2 [256]   pixel centre
+constexpr uint32_t kOffRec = kOffPxy + 256 * 8;           // [2][kB2 * 48]  staged GaussRec
+constexpr uint32_t kOffId = kOffRec + 2 * kB2 * kRec2;    // u32 [2][kB2]
+constexpr uint32_t kOffMask = kOffId + 2 * kB2 * 4;       // u32 [8]        per-warp "slot has contributions" bits
+constexpr uint32_t kSmem2 = kOffMask + 8 * 4;
+
+__device__ __forceinline__ float4 ld4(uint32_t a) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ float2 ld2(uint32_t a) {
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldu(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void st4(uint32_t a, float4 v) {
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ void stu(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
+                                                         const uint32_t *__restrict__ point_list, const GaussRec *__restrict__ rec,
+                                                         const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tile_max_contrib,
+                                                         const float *__restrict__ alphas, const float *__restrict__ dL_dpixels,
+                                                         const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dalphas,
+                                                         float *__restrict__ grad2d) {
+	extern __shared__ __align__(16) unsigned char smem2[];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int tile_x = blockIdx.x, tile_y = f.band.begin + blockIdx.y * f.band.step;
+	const int tile = tile_y * f.gx + tile_x;
+	const int n_eff = (int)tile_max_contrib[tile];
+	if (n_eff == 0) return;
+	const int px = tile_x * SGR_TILE + (warp & 1) * 8 + (lane & 7);
+	const int py = tile_y * SGR_TILE + (warp >> 1) * 4 + (lane >> 3);
+	const bool inside = px < f.W && py < f.H;
+	const size_t HW = (size_t)f.W * f.H;
+	const size_t pix_id = (size_t)f.W * py + px;
+	const float2 pixf = make_float2((float)px, (float)py);
+	const uint32_t list0 = ranges[tile].x;
+	const int nb = (n_eff + kB2 - 1) / kB2;
+	const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem2);
+
+	const float T_final = inside ? (1 - alphas[pix_id]) : 0;
+	float T = T_final;
+	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+	float accum_rec[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, dL_dpixel[3] = {0, 0, 0};
+	float accum_depth_rec = 0, last_depth = 0, accum_alpha_rec = 0, last_alpha = 0;
+	float dL_dpixel_depth = 0, dL_dalpha_px = 0;
+	if (inside) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) dL_dpixel[c] = dL_dpixels[c * HW + pix_id];
+		dL_dpixel_depth = dL_dpixel_depths[pix_id];
+		dL_dalpha_px = dL_dalphas[pix_id];
+	}
+	float bg_dot_dpixel = 0;
+#pragma unroll
+	for (int c = 0; c < 3; c++) bg_dot_dpixel += f.bg[c] * dL_dpixel[c];
+	const float kW = 0.5f * f.W, kH = 0.5f * f.H;  // d(pixel)/d(NDC), reference backward.cu:501-502
+	st4(sb + kOffPix + (uint32_t)tid * 16u, make_float4(dL_dpixel[0], dL_dpixel[1], dL_dpixel[2], dL_dpixel_depth));
+	st2(sb + kOffPxy + (uint32_t)tid * 8u, pixf.x, pixf.y);
+
+	// staging: 4 threads per record (q0, q1, q2, id), threads 0..127; slot j of batch b <-> list index (n_eff - b*B) - 1 - j
+	const int ld_slot = tid >> 2, ld_part = tid & 3;
+	float4 rq = make_float4(0, 0, 0, 0);
+	uint32_t rid = 0;
+	auto fetch = [&](int b) {
+		const int idx = n_eff - b * kB2 - 1 - ld_slot;
+		if (ld_slot < kB2 && idx >= 0) {
+			rid = point_list[list0 + idx];
+			if (ld_part < 3) rq = reinterpret_cast<const float4 *>(rec + rid)[ld_part];
+		}
+	};
+	auto stash = [&](int buf) {
+		if (ld_slot < kB2) {
+			if (ld_part < 3) st4(sb + kOffRec + (uint32_t)buf * (kB2 * kRec2) + (uint32_t)ld_slot * kRec2 + (uint32_t)ld_part * 16u, rq);
+			else stu(sb + kOffId + (uint32_t)(buf * kB2 + ld_slot) * 4u, rid);
+		}
+	};
+	fetch(0);
+	stash(0);
+
+	// phase-2 role of this thread
+	const int p2_slot = tid >> 3, p2_chunk = tid & 7;
+
+	for (int b = 0; b < nb; b++) {
+		__syncthreads();  // record buffer b&1 published; phase 2 of the previous batch is done with s_wq / s_mask
+		if (b + 1 < nb) fetch(b + 1);
+		const int buf = b & 1;
+		const int hi = n_eff - b * kB2;  // list position (1-based) of slot 0
+		const int cnt = min(kB2, hi);
+		const uint32_t rbase = sb + kOffRec + (uint32_t)buf * (kB2 * kRec2);
+
+		// ---------------- phase 1: per-pixel recurrences -> (w, q) ----------------
+		uint32_t wmask = 0u;
+		uint32_t a = rbase;
+		uint32_t wq_addr = sb + kOffWQ + (uint32_t)tid * 8u;
+		for (int j = 0; j < cnt; j++, a += kRec2, wq_addr += 256u * 8u) {
+			const int contributor = hi - 1 - j;
+			bool valid = contributor < last_contributor;
+			float q = 0.f, w = 0.f;
+			if (valid) {
+				const float4 q0 = ld4(a);       // pix.x, pix.y, conic.xx, conic.xy
+				const float4 q1 = ld4(a + 16);  // conic.yy, opacity, power_min, depth
+				const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
+				const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
+				valid = !(power > 0.0f) && !(power < q1.z);
+				if (valid) {
+					const float G = expf(power);
+					const float alpha = fminf(0.99f, q1.y * G);
+					valid = !(alpha < 1.0f / 255.0f);
+					if (valid) {
+						const float4 q2 = ld4(a + 32);  // r, g, b, clamp bits
+						const float inv = 1.0f / (1.f - alpha);
+						T = T * inv;
+						w = alpha * T;
+						const float oml = 1.f - last_alpha;
+						float dL_dopa = 0.0f;
+						const float col[3] = {q2.x, q2.y, q2.z};
+#pragma unroll
+						for (int ch = 0; ch < 3; ch++) {
+							accum_rec[ch] = last_alpha * last_color[ch] + oml * accum_rec[ch];
+							last_color[ch] = col[ch];
+							dL_dopa += (col[ch] - accum_rec[ch]) * dL_dpixel[ch];
+						}
+						accum_depth_rec = last_alpha * last_depth + oml * accum_depth_rec;
+						last_depth = q1.w;
+						dL_dopa += (q1.w - accum_depth_rec) * dL_dpixel_depth;
+						accum_alpha_rec = last_alpha + oml * accum_alpha_rec;
+						dL_dopa += (1 - accum_alpha_rec) * dL_dalpha_px;
+						dL_dopa *= T;
+						last_alpha = alpha;
+						dL_dopa += (-T_final * inv) * bg_dot_dpixel;
+						q = q1.y * (G * dL_dopa);  // G * dL/dG
+					}
+				}
+			}
+			if (__ballot_sync(0xffffffffu, valid) != 0u) {  // warp-uniform
+				st2(wq_addr, w, q);
+				wmask |= 1u << j;
+			}
+		}
+		if (lane == 0) stu(sb + kOffMask + (uint32_t)warp * 4u, wmask);
+		__syncthreads();
+
+		// ---------------- phase 2: per-splat sums over the tile's pixels ----------------
+		{
+			float Sq = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sabs = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
+			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (uint32_t)p2_chunk * 4u) >> p2_slot) & 1u);
+			float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+			if (live) {
+				r0 = ld4(rbase + (uint32_t)p2_slot * kRec2);
+				r1 = ld4(rbase + (uint32_t)p2_slot * kRec2 + 16);
+				const uint32_t row = sb + kOffWQ + (uint32_t)(p2_slot * 256 + p2_chunk * 32) * 8u;
+				const uint32_t pixb = sb + kOffPix + (uint32_t)(p2_chunk * 32) * 16u;
+				const uint32_t pxyb = sb + kOffPxy + (uint32_t)(p2_chunk * 32) * 8u;
+#pragma unroll 4
+				for (int i = 0; i < 32; i++) {
+					const uint32_t l = (uint32_t)(i + lane) & 31u;  // bank rotation: the 32 lanes of a warp hit 32 distinct pixels
+					const float2 wq = ld2(row + l * 8u);
+					const float4 pg = ld4(pixb + l * 16u);
+					const float2 pc = ld2(pxyb + l * 8u);
+					const float dx = r0.x - pc.x, dy = r0.y - pc.y;
+					const float qx = wq.y * dx, qy = wq.y * dy;
+					Sq += wq.y;
+					Sx += qx;
+					Sy += qy;
+					Sxx += qx * dx;
+					Sxy += qx * dy;
+					Syy += qy * dy;
+					Sabs += fabsf(wq.y) * (fabsf(r0.z * dx + r0.w * dy) * kW + fabsf(r1.x * dy + r0.w * dx) * kH);
+					Cr += wq.x * pg.x;
+					Cg += wq.x * pg.y;
+					Cb += wq.x * pg.z;
+					Cd += wq.x * pg.w;
+				}
+			}
+			// combine the 8 chunk-threads of each splat (consecutive lanes) — all lanes take part
+			const unsigned any_live = __ballot_sync(0xffffffffu, live);
+			if (any_live) {
+#pragma unroll
+				for (int o = 1; o < 8; o <<= 1) {
+					Sq += __shfl_xor_sync(0xffffffffu, Sq, o); Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
+					Sy += __shfl_xor_sync(0xffffffffu, Sy, o); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
+					Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o); Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
+					Sabs += __shfl_xor_sync(0xffffffffu, Sabs, o); Cr += __shfl_xor_sync(0xffffffffu, Cr, o);
+					Cg += __shfl_xor_sync(0xffffffffu, Cg, o); Cb += __shfl_xor_sync(0xffffffffu, Cb, o);
+					Cd += __shfl_xor_sync(0xffffffffu, Cd, o);
+				}
+				// is any chunk of this splat live?  (bits of the 8 lanes of this slot in the ballot)
+				const unsigned grp = (any_live >> (lane & 24)) & 0xffu;
+				// the conic / opacity of the splat: lanes that were not live did not load the record (all lanes shuffle)
+				const int srcl = grp != 0u ? (lane & 24) + (__ffs(grp) - 1) : lane;
+				const float ca = __shfl_sync(0xffffffffu, r0.z, srcl), cb = __shfl_sync(0xffffffffu, r0.w, srcl);
+				const float cc = __shfl_sync(0xffffffffu, r1.x, srcl), op = __shfl_sync(0xffffffffu, r1.y, srcl);
+				if (grp != 0u && p2_slot < cnt) {
+					const uint32_t gid = ldu(sb + kOffId + (uint32_t)(buf * kB2 + p2_slot) * 4u);
+					float *dst = grad2d + (size_t)gid * 12;
+					float o0, o1 = 0.f;
+					switch (p2_chunk) {  // lane c of the group writes components c and c + 8
+						case 0: o0 = -kW * (ca * Sx + cb * Sy); o1 = Cg; break;
+						case 1: o0 = -kH * (cc * Sy + cb * Sx); o1 = Cb; break;
+						case 2: o0 = Sabs; o1 = Cd; break;
+						case 3: o0 = -0.5f * Sxx; break;
+						case 4: o0 = -0.5f * Sxy; break;
+						case 5: o0 = -0.5f * Syy; break;
+						case 6: o0 = (op != 0.f) ? Sq / op : 0.f; break;
+						default: o0 = Cr; break;
+					}
+					atomicAdd(dst + p2_chunk, o0);
+					if (p2_chunk < 3) atomicAdd(dst + 8 + p2_chunk, o1);
+				}
+			}
+		}
+		if (b + 1 < nb) stash((b + 1) & 1);
+	}
+}
+
+cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *out_alpha, const float *dL_dcolor,
+                              const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(grad2d, 0, (size_t)f.P * 12 * sizeof(float), st);
+	if (e != cudaSuccess) return e;
+	const int rows = band_rows(f.band);
+	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
+	static bool configured = false;
+	if (!configured) {
+		e = cudaFuncSetAttribute(blend_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
+		if (e != cudaSuccess) return e;
+		configured = true;
+	}
+	blend_bwd2_kernel<<<dim3(f.gx, rows), 256, kSmem2, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, img.tile_max_contrib, out_alpha,
+	                                                         dL_dcolor, dL_ddepth, dL_dalpha, grad2d);
+	return cudaGetLastError();
+}
+
+}  // namespace sgr

@@ -36,6 +36,8 @@ GeomView carve_geom(void *base, int P) {
 	g.depth_sorted = take<uint32_t>(p, n);
 	g.perm = take<uint32_t>(p, n);
 	g.offsets = take<uint32_t>(p, n);
+	g.big_list = take<uint32_t>(p, n);
+	g.big_count = take<uint32_t>(p, 64);
 	g.temp_bytes = geom_temp_bytes(P);
 	g.temp = take<char>(p, g.temp_bytes);
 	g.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));

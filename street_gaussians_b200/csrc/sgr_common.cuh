@@ -34,6 +34,8 @@ struct GeomView {
 	uint32_t *depth_sorted;   // sorted depth keys (scratch)
 	uint32_t *perm;           // Gaussian indices in ascending (depth, index) order
 	uint32_t *offsets;        // inclusive scan of tiles_touched[perm[.]]  (depth order)
+	uint32_t *big_list;       // depth-order positions of Gaussians whose rectangle is emitted by a whole warp (emit_big_kernel)
+	uint32_t *big_count;      // number of entries in big_list (device counter, zeroed per forward)
 	void *temp;               // cub temp storage: max(scan, depth sort)
 	size_t temp_bytes;
 	size_t total_bytes;
@@ -154,6 +156,8 @@ cudaError_t launch_blend_fwd(const FrameDev &f, GeomView g, BinView b, ImgView i
 cudaError_t launch_blend_bwd(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *semantics,
                              const float *out_alpha, const float *dL_dcolor, const float *dL_ddepth, const float *dL_dalpha,
                              const float *dL_dsem, float *grad2d, float *dL_dsemantics, cudaStream_t st);
+cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *out_alpha, const float *dL_dcolor,
+                              const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st);
 cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
                                   const float *scales, const float *rotations, const float *cov3D_precomp,
                                   const int32_t *radii, GeomView g, const float *grad2d, float *dL_dmeans3D,

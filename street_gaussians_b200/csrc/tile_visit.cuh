@@ -85,7 +85,8 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
                                             int gx, uint32_t gauss_idx, uint32_t offset, KeyT *__restrict__ keys,
                                             uint32_t *__restrict__ vals, uint32_t &count, KeyT *stage_keys = nullptr,
                                             uint32_t *stage_vals = nullptr, uint32_t stage_cap = 0, uint32_t warp_first = 0,
-                                            uint32_t warp_total = 0) {
+                                            uint32_t warp_total = 0, uint32_t *big_list = nullptr, uint32_t *big_count = nullptr,
+                                            uint32_t big_tag = 0) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	if (active) {
@@ -98,11 +99,23 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 	const EllipseAux ea = ellipse_aux(cp);
 	count = 0;
 	unsigned todo = __ballot_sync(full, coop);
+	if (EMIT && big_list != nullptr && todo != 0u) {
+		// Defer large rectangles to emit_big_kernel (one warp per Gaussian, spread over the whole GPU).  In depth order the
+		// nearest = largest splats sit next to each other; a warp that had to walk 32 of them serially ran for the whole
+		// kernel (ncu: busiest SM 492k cycles vs 234k mean) while the rest of the chip idled.
+		const uint32_t n_big = (uint32_t)__popc(todo);
+		uint32_t base = 0;
+		if (lane == 0) base = atomicAdd(big_count, n_big);
+		base = __shfl_sync(full, base, 0);
+		if (coop) big_list[base + (uint32_t)__popc(todo & ((1u << lane) - 1u))] = big_tag;
+		todo = 0u;
+	}
+	const bool any_coop = __ballot_sync(full, coop) != 0u;
 	// Emission of a warp's 32 (depth-consecutive) Gaussians covers ONE contiguous output range.  When it fits the
 	// per-warp shared-memory stage (and no lane needs the cooperative path) the lanes scatter into shared memory and the
 	// warp then copies the range out with fully coalesced stores; per-thread global scatter (32 sectors per store
 	// instruction) is the fallback.
-	const bool staged = EMIT && stage_keys != nullptr && todo == 0u && warp_total <= stage_cap;
+	const bool staged = EMIT && stage_keys != nullptr && !any_coop && warp_total <= stage_cap;
 	if (active && !coop) {
 		uint32_t off = offset;
 		for (int ty = y0; ty < y1; ty++) {
