@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 	const float T_final = inside ? (1 - alphas[pix_id]) : 0;
 	float T = T_final;
 	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
-	float accum_rec[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, dL_dpixel[3] = {0, 0, 0};
-	float accum_depth_rec = 0, last_depth = 0, accum_alpha_rec = 0, last_alpha = 0;
+	float dL_dpixel[3] = {0, 0, 0};
+	float behind = 0.f, g_last = 0.f, last_alpha = 0.f;  // scalar form of the reference's accum_rec / last_color family
 	float dL_dpixel_depth = 0, dL_dalpha_px = 0;
 	if (inside) {
 #pragma unroll
@@ -141,26 +141,20 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 					valid = !(alpha < 1.0f / 255.0f);
 					if (valid) {
 						const float4 q2 = ld4(a + 32);  // r, g, b, clamp bits
-						const float inv = 1.0f / (1.f - alpha);
+						const float inv = 1.0f / (1.f - alpha);  // one IEEE division serves T/(1-a) and T_final/(1-a)
 						T = T * inv;
 						w = alpha * T;
-						const float oml = 1.f - last_alpha;
-						float dL_dopa = 0.0f;
-						const float col[3] = {q2.x, q2.y, q2.z};
-#pragma unroll
-						for (int ch = 0; ch < 3; ch++) {
-							accum_rec[ch] = last_alpha * last_color[ch] + oml * accum_rec[ch];
-							last_color[ch] = col[ch];
-							dL_dopa += (col[ch] - accum_rec[ch]) * dL_dpixel[ch];
-						}
-						accum_depth_rec = last_alpha * last_depth + oml * accum_depth_rec;
-						last_depth = q1.w;
-						dL_dopa += (q1.w - accum_depth_rec) * dL_dpixel_depth;
-						accum_alpha_rec = last_alpha + oml * accum_alpha_rec;
-						dL_dopa += (1 - accum_alpha_rec) * dL_dalpha_px;
-						dL_dopa *= T;
+						// The reference keeps one "value behind" accumulator per blended quantity (3 colours, depth, the constant 1
+						// of the alpha channel), all with the SAME recurrence  acc <- last_alpha*last_q + (1-last_alpha)*acc, and
+						// only ever uses them dotted with this pixel's upstream gradients (backward.cu:563-602).  The dot product
+						// commutes with the recurrence, so ONE scalar suffices:
+						//   g_i = c_i . dL/dC + depth_i * dL/dD + 1 * dL/dA,   A <- last_alpha * g_last + (1-last_alpha) * A,
+						//   dL/dalpha_i = (g_i - A) * T_i + bg term.
+						const float g = q2.x * dL_dpixel[0] + q2.y * dL_dpixel[1] + q2.z * dL_dpixel[2] + q1.w * dL_dpixel_depth + dL_dalpha_px;
+						behind = last_alpha * g_last + (1.f - last_alpha) * behind;
+						g_last = g;
 						last_alpha = alpha;
-						dL_dopa += (-T_final * inv) * bg_dot_dpixel;
+						const float dL_dopa = (g - behind) * T + (-T_final * inv) * bg_dot_dpixel;
 						q = q1.y * (G * dL_dopa);  // G * dL/dG
 					}
 				}
