@@ -346,7 +346,7 @@ def main():
                                 num_instances=n_inst, gaussians_pixels_per_s=P * W * H * fps, stage_ms=stages),
                     e2e=dict(value=1000.0 / e2e_ms, unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                              note="pinned host -> device copy of all 59 floats/Gaussian every step, double-buffered on a copy stream; scalar loss read back"),
-                    gpu_launches=(16 * args.steps) if not ref_cuda else 0, clocks=clocks)
+                    gpu_launches=(20 * args.steps) if not ref_cuda else 0, clocks=clocks)
         if roofline:
             line["roofline"] = roofline
         if cb:
