@@ -278,7 +278,7 @@ def main():
         alg_bytes = n_inst * 44 + npx * rows_frac * 28 + visible * 44
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (stages["blend_bwd"] * 1e-3) / 1e9
-        roofline = dict(bound="hbm", kernel="blend_bwd_kernel<0>", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+        roofline = dict(bound="hbm", kernel="blend_bwd2_kernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                         traffic=None, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
                         note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the "
                              "contract asks; kernel_ms includes two cudaMemsetAsync of the accumulators")

@@ -58,13 +58,15 @@ with open(os.path.join(out_dir, f"{tag}_ncu_full.md"), "w") as f:
             sh = srows[1]; six = {h: i for i, h in enumerate(sh)}
             if "Instructions Executed" not in six:
                 continue
-            tot = sum(int(r[six["Instructions Executed"]]) for r in srows[2:] if r[six["Instructions Executed"]].isdigit())
+            ie = six["Instructions Executed"]
+            body = [r for r in srows[2:] if len(r) > ie and r[ie].isdigit()]
+            tot = sum(int(r[ie]) for r in body)
+            if tot == 0:
+                continue
             ops = collections.Counter()
-            for r in srows[2:]:
-                if not r[six["Instructions Executed"]].isdigit():
-                    continue
+            for r in body:
                 s = r[six["Source"]].strip().split()
-                op = (s[1] if s and s[0].startswith("@") else (s[0] if s else "?")).split(".")[0]
+                op = (s[1] if len(s) > 1 and s[0].startswith("@") else (s[0] if s else "?")).split(".")[0]
                 ops[op] += int(r[six["Instructions Executed"]])
             f.write(f"### {nm}: {tot} warp-instructions executed; top opcodes: " + ", ".join(f"{k} {100*v/tot:.1f}%" for k, v in ops.most_common(12)) + "\n\n")
 print("wrote profiles/", tag)
