@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--impl", default="sgr", choices=["sgr", "reference"])
     ap.add_argument("--workload", default="C", choices=list(synthetic.CONFIGS.keys()))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffer) leg")
+    ap.add_argument("--no-clock-sampler", action="store_true")
+    ap.add_argument("--diag", action="store_true", help="per-rank host/all-reduce timing breakdown on stderr")
     ap.add_argument("--cpu-sample-stride", type=int, default=0, help="CPU baseline uses every k-th Gaussian (0 = auto)")
     return ap.parse_args()
 
@@ -227,19 +230,40 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clock_sampler) else None
+    diag = {"ar": [], "host": []}
+    if args.diag and use_dist and rast.grad_reduce is not None:
+        inner = rast.grad_reduce
+
+        def timed_reduce(g2d, gsem):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = inner(g2d, gsem)
+            b.record()
+            diag["ar"].append((a, b))
+            return out
+
+        rast.grad_reduce = timed_reduce
     for _ in range(max(args.warmup, 3)):
         step()
+    diag["ar"].clear()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.mark(0)
     e0.record()
     for _ in range(args.steps):
+        t_h = time.perf_counter()
         color, radii = step()
+        diag["host"].append((time.perf_counter() - t_h) * 1e3)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    if args.diag:
+        ar = [a.elapsed_time(b) for a, b in diag["ar"]]
+        print(f"[diag rank {rank}] step {ms_total / args.steps:.3f} ms | host loop per step: median {np.median(diag['host']):.3f} max {max(diag['host']):.3f} ms"
+              + (f" | all-reduce (device, incl. waiting for peers): median {np.median(ar):.3f} min {min(ar):.3f} max {max(ar):.3f} ms" if ar else ""),
+              file=sys.stderr, flush=True)
     if use_dist:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -284,6 +308,18 @@ def main():
                              "contract asks; kernel_ms includes two cudaMemsetAsync of the accumulators")
 
     # ---- end to end from pinned host memory ----
+    if args.no_e2e:
+        if sampler:
+            sampler.mark(1)
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            fps = 1000.0 / ms_step
+            print(json.dumps(dict(metric="rasterizer_fwd_bwd_fps", value=fps, unit="frames/s", n_gpus=world if use_dist else 1, steps=args.steps,
+                                  warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong", dtype="f32",
+                                  config=dict(workload=wl_desc, stage_ms=stages), clocks=clocks, note="--no-e2e diagnostic line")))
+        if use_dist:
+            dist.destroy_process_group()
+        return 0
     host = {k: scene[k].pin_memory() for k in PARAM_KEYS}
     h2d_bytes = sum(v.numel() * 4 for v in host.values())
     copy_stream = torch.cuda.Stream(device=dev)
