@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGR_ABI_VERSION 1
+#define SGR_ABI_VERSION 2
 
 #define SGR_OK 0
 #define SGR_EINVAL (-1)   /* bad argument combination / shape                     */
@@ -96,6 +96,25 @@ int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, c
                 const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
                 int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
                 void *alloc_user, void **binning_state, int64_t *num_instances, void *stream);
+
+/* Forward without any host synchronisation ("R read back asynchronously or bounded").  Identical to
+ * sgr_forward except that the CALLER supplies the binning state, sized with sgr_binning_bytes(capacity), instead of the
+ * library reading the instance count back to size it.  The count stays on the device: instances beyond `capacity` are
+ * dropped (whole Gaussians, farthest first) and an overflow flag is raised in img_state — the frame is then incomplete,
+ * and the caller must re-render with a larger capacity.  sgr_forward_status() fetches {instances, overflowed} when the
+ * caller chooses to synchronise (e.g. once per N frames, or before the optimiser step).  Pass `capacity` as
+ * num_instances to the sgr_backward_* calls.  No reference counterpart: the reference always blocks on a cudaMemcpy
+ * (DGR/cuda_rasterizer/rasterizer_impl.cu:283-284). */
+int sgr_forward_bounded(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                        const float *semantics, const float *opacities, const float *scales, const float *rotations,
+                        const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
+                        int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes,
+                        void *binning_state, size_t binning_bytes, int64_t capacity, void *stream);
+/* Device->host copy of the status words of the last forward that used geom_state; synchronises `stream`. */
+int sgr_forward_status(const SgrFrame *frame, const void *geom_state, int64_t *num_instances, int32_t *overflowed, void *stream);
+/* Asynchronous variant: enqueues the copy of two uint32 {instances, overflowed} into host_status (pinned host memory
+ * recommended) on `stream` and returns immediately; valid once the caller has observed stream progress past this point. */
+int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream);
 
 /* Backward, stage 1 of 2: per-pixel backward blend.  Replaces BACKWARD::render
  * (DGR/cuda_rasterizer/backward.cu:415-641, called at rasterizer_impl.cu:454-477).

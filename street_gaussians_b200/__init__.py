@@ -10,10 +10,10 @@ from __future__ import annotations
 import os
 import sys
 
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, TileRowBand, distCUDA2,  # noqa: F401
-                         rasterize_gaussians)
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, InstanceCapacity, TileRowBand,  # noqa: F401
+                         distCUDA2, rasterize_gaussians)
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "TileRowBand", "rasterize_gaussians", "distCUDA2",
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "TileRowBand", "InstanceCapacity", "rasterize_gaussians", "distCUDA2",
            "install_shims"]
 
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")

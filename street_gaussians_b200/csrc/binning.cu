@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
                                                         const uint32_t *__restrict__ /*tiles_touched*/, const uint32_t *__restrict__ perm,
                                                         const uint32_t *__restrict__ offsets, KeyT *__restrict__ keys,
                                                         uint32_t *__restrict__ vals, uint32_t *__restrict__ big_list,
-                                                        uint32_t *__restrict__ big_count) {
+                                                        uint32_t *__restrict__ big_count, const uint32_t cap) {
 	__shared__ KeyT s_keys[8][kEmitStage];
 	__shared__ uint32_t s_vals[8][kEmitStage];
 	const int warp = threadIdx.x >> 5;
@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 	uint32_t end = offsets[tc];
 	uint32_t off = tc == 0 ? 0u : offsets[tc - 1];
 	if (t >= f.P) off = end;
+	if (end > cap) end = off;  // bounded mode: a Gaussian whose range does not fit the caller's capacity emits nothing
 	if (t < f.P) {
 		gidx = perm[t];
 		if (end > off) {
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 		}
 	}
 	const uint32_t warp_first = __shfl_sync(0xffffffffu, off, 0);
-	const uint32_t warp_total = __shfl_sync(0xffffffffu, end, 31) - warp_first;
+	const uint32_t warp_last = __shfl_sync(0xffffffffu, end, 31);
+	const uint32_t warp_total = warp_last >= warp_first ? warp_last - warp_first : 0xffffffffu;  // (overflow tail: no staging)
 	uint32_t count;
 	visit_tiles<true, KeyT>(active, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count, s_keys[warp], s_vals[warp], kEmitStage,
 	                  warp_first, warp_total, big_list, big_count, (uint32_t)t);
@@ -97,7 +99,8 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_big_kernel(const FrameDev f, const GaussRec *__restrict__ rec, const int32_t *__restrict__ radii,
                                                       const uint32_t *__restrict__ perm, const uint32_t *__restrict__ offsets,
                                                       KeyT *__restrict__ keys, uint32_t *__restrict__ vals,
-                                                      const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count) {
+                                                      const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
+                                                      const uint32_t cap) {
 	const uint32_t n = *big_count;
 	const uint32_t nwarps = gridDim.x * 8u;
 	const int lane = threadIdx.x & 31;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) emit_big_kernel(const FrameDev f, const G
 		tile_rect(q0.x, q0.y, radii[gidx], f.gx, f.gy, x0, y0, x1, y1);
 		const CullParams cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
 		const uint32_t off = t == 0 ? 0u : offsets[t - 1];
+		if (offsets[t] > cap) continue;  // bounded mode overflow (never deferred in practice: emit_pairs already skipped it)
 		// lane 0 carries the Gaussian through the cooperative path of visit_tiles (all other lanes inactive)
 		uint32_t count;
 		visit_tiles<true, KeyT>(lane == 0, x0, y0, x1, y1, cp, f.band, f.gx, gidx, off, keys, vals, count);
@@ -118,20 +122,47 @@ __global__ void __launch_bounds__(256) emit_big_kernel(const FrameDev f, const G
 // One thread per sorted instance: a tile's range starts / ends where the tile id changes
 // (reference identifyTileRanges, rasterizer_impl.cu:116-138).  ranges must be zero-initialised.
 template <typename KeyT>
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const KeyT *__restrict__ keys, uint2 *__restrict__ ranges) {
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const KeyT *__restrict__ keys, uint2 *__restrict__ ranges, const uint32_t ntile) {
 	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= L) return;
+	// keys >= ntile are the padding of the bounded mode (they sort behind every real tile)
 	const uint32_t cur = keys[idx];
-	if (idx == 0)
-		ranges[cur].x = 0;
-	else {
+	if (idx == 0) {
+		if (cur < ntile) ranges[cur].x = 0;
+	} else {
 		const uint32_t prev = keys[idx - 1];
 		if (cur != prev) {
-			ranges[prev].y = (uint32_t)idx;
-			ranges[cur].x = (uint32_t)idx;
+			if (prev < ntile) ranges[prev].y = (uint32_t)idx;
+			if (cur < ntile) ranges[cur].x = (uint32_t)idx;
 		}
 	}
-	if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+	if (idx == L - 1 && cur < ntile) ranges[cur].y = (uint32_t)L;
+}
+
+// status words: [1] = R (true instance count), [2] = overflow flag, [3] = instances actually emitted (<= cap)
+__global__ void count_status_kernel(const uint32_t *__restrict__ offsets, int P, uint32_t cap, uint32_t *__restrict__ status) {
+	const uint32_t R = offsets[P - 1];
+	uint32_t emitted = R;
+	if (R > cap) {  // largest scanned offset that still fits: Gaussians are emitted in depth order, the tail is dropped
+		int lo = 0, hi = P;  // first index with offsets[i] > cap
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			if (offsets[mid] > cap) hi = mid; else lo = mid + 1;
+		}
+		emitted = lo == 0 ? 0u : offsets[lo - 1];
+	}
+	status[1] = R;
+	status[2] = R > cap ? 1u : 0u;
+	status[3] = emitted;
+}
+template <typename KeyT>
+__global__ void __launch_bounds__(256) pad_keys_kernel(KeyT *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t cap,
+                                                      const uint32_t *__restrict__ status) {
+	const uint32_t i = status[3] + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < cap) {
+		keys[i] = (KeyT)~(KeyT)0;
+		vals[i] = 0u;
+	}
 }
 
 static int bits_for(uint32_t n) {  // smallest b with (1 << b) >= n, i.e. enough bits for tile ids 0..n-1
@@ -140,30 +171,41 @@ static int bits_for(uint32_t n) {  // smallest b with (1 << b) >= n, i.e. enough
 	return b > 0 ? b : 1;
 }
 
-cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, BinView b, ImgView img, int64_t R, cudaStream_t st) {
+cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, BinView b, ImgView img, int64_t R, cudaStream_t st,
+                           int64_t cap) {
 	const int ntile = f.gx * f.gy;
+	const bool bounded = cap >= 0;
 	cudaError_t e = cudaMemsetAsync(img.ranges, 0, (size_t)ntile * sizeof(uint2), st);
 	if (e != cudaSuccess) return e;
-	if (R == 0 || f.P == 0) return cudaSuccess;
+	if (f.P == 0) return cudaSuccess;
+	const uint32_t cap32 = bounded ? (uint32_t)cap : 0xffffffffu;
+	count_status_kernel<<<1, 1, 0, st>>>(g.offsets, f.P, cap32, g.big_count);
+	if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	if (bounded) R = cap;  // every pass below runs over the caller's capacity; the padding carries the largest key
+	if (R == 0) return cudaSuccess;
 	size_t bytes = b.sort_temp_bytes;
 	const unsigned nblk = (unsigned)((f.P + 255) / 256);
 	const unsigned nbig_blk = 148 * 4;  // persistent-style grid for the deferred large rectangles
 	if ((e = cudaMemsetAsync(g.big_count, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
-	if (ntile <= 65536) {  // 16-bit tile ids (the key arrays are allocated for 32-bit ids either way)
+	const unsigned npad_blk = bounded ? (unsigned)((cap + 255) / 256) : 0u;  // upper bound; threads past `cap` exit
+	const int sort_bits = bounded ? (ntile <= 65535 ? 16 : 32) : bits_for(ntile);
+	if (ntile <= 65535 || (!bounded && ntile <= 65536)) {  // 16-bit tile ids (the key arrays are allocated for 32-bit ids either way)
 		uint16_t *kin = reinterpret_cast<uint16_t *>(b.keys_in), *kout = reinterpret_cast<uint16_t *>(b.keys_out);
-		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count);
-		emit_big_kernel<uint16_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count);
+		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32);
+		emit_big_kernel<uint16_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32);
+		if (bounded) pad_keys_kernel<uint16_t><<<npad_blk, 256, 0, st>>>(kin, b.vals_in, cap32, g.big_count);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
-		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, kin, kout, b.vals_in, b.vals_out, R, 0, bits_for(ntile), st);
+		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, kin, kout, b.vals_in, b.vals_out, R, 0, sort_bits, st);
 		if (e != cudaSuccess) return e;
-		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, kout, img.ranges);
+		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, kout, img.ranges, (uint32_t)ntile);
 	} else {
-		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count);
-		emit_big_kernel<uint32_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count);
+		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
+		emit_big_kernel<uint32_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
+		if (bounded) pad_keys_kernel<uint32_t><<<npad_blk, 256, 0, st>>>(b.keys_in, b.vals_in, cap32, g.big_count);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
-		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, R, 0, bits_for(ntile), st);
+		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, R, 0, sort_bits, st);
 		if (e != cudaSuccess) return e;
-		tile_ranges_kernel<uint32_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, b.keys_out, img.ranges);
+		tile_ranges_kernel<uint32_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, b.keys_out, img.ranges, (uint32_t)ntile);
 	}
 	return cudaGetLastError();
 }

@@ -2,6 +2,7 @@
 // Host-side only; every device kernel lives in its own translation unit.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sgr_common.cuh"
@@ -93,6 +94,37 @@ static int check(cudaError_t e, const char *what, bool debug, cudaStream_t st) {
 	if (e != cudaSuccess) return fail(SGR_ECUDA, "%s: %s", what, cudaGetErrorString(e));
 	return SGR_OK;
 }
+// The one host<->device round trip of the exact mode: 4 bytes into a pinned, thread-local staging word, then a
+// BLOCKING wait on an event (the thread sleeps instead of spinning in cudaStreamSynchronize).  With one process per GPU
+// on a box whose container has fewer host cores than 2 x GPUs (this pool: cgroup quota of 16 cores for 8 GPUs) eight
+// spinning main threads plus eight autograd threads exhaust the quota and every rank gets throttled — measured as the
+// N=8 step time being 1.5 ms above the sum of its stages (profiles/r01_summary.md §5).  SGR_SYNC_MODE=spin restores the
+// lower-latency busy wait for single-GPU use.
+static cudaError_t read_back_u32(uint32_t *dst, const uint32_t *src_dev, cudaStream_t st) {
+	static thread_local uint32_t *pinned = nullptr;
+	static thread_local cudaEvent_t ev = nullptr;
+	static thread_local int ev_dev = -1;
+	static const bool spin = [] { const char *m = getenv("SGR_SYNC_MODE"); return m && strcmp(m, "spin") == 0; }();
+	cudaError_t e;
+	if (!pinned && (e = cudaHostAlloc(reinterpret_cast<void **>(&pinned), 64, cudaHostAllocDefault)) != cudaSuccess) return e;
+	int dev = 0;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+	if (!spin && (ev == nullptr || ev_dev != dev)) {
+		if (ev) cudaEventDestroy(ev);
+		if ((e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return e;
+		ev_dev = dev;
+	}
+	if ((e = cudaMemcpyAsync(pinned, src_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+	if (spin) {
+		if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+	} else {
+		if ((e = cudaEventRecord(ev, st)) != cudaSuccess) return e;
+		if ((e = cudaEventSynchronize(ev)) != cudaSuccess) return e;
+	}
+	*dst = *pinned;
+	return cudaSuccess;
+}
+
 #define SGR_TRY(expr, what)                                             \
 	do {                                                                \
 		int rc_ = check((expr), what, debug, st);                       \
@@ -119,16 +151,20 @@ int sgr_state_sizes(const SgrFrame *frame, size_t *geom_bytes, size_t *img_bytes
 
 size_t sgr_binning_bytes(int64_t R) { return carve_bin(nullptr, R).total_bytes; }
 
-int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
-                const float *semantics, const float *opacities, const float *scales, const float *rotations,
-                const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
-                int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
-                void *alloc_user, void **binning_state, int64_t *num_instances, void *stream) {
+// shared body of sgr_forward (exact: reads the instance count back, asks the caller's allocator) and sgr_forward_bounded
+// (no host synchronisation: caller-sized binning state, count stays on the device)
+static int forward_impl(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                        const float *semantics, const float *opacities, const float *scales, const float *rotations,
+                        const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
+                        int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
+                        void *alloc_user, void **binning_state, int64_t *num_instances, void *bounded_state, size_t bounded_bytes,
+                        int64_t capacity, void *stream) {
 	FrameDev f;
 	int rc = make_frame(frame, f);
 	if (rc) return rc;
 	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 	const bool debug = frame->debug != 0;
+	const bool bounded = capacity >= 0;
 	if (binning_state) *binning_state = nullptr;
 	if (num_instances) *num_instances = 0;
 	if (!out_color || !out_depth || !out_alpha || (f.S > 0 && !out_semantic)) return fail(SGR_EINVAL, "output image pointer is NULL");
@@ -146,6 +182,12 @@ int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, c
 	const ImgView img = carve_img(img_state, f.W, f.H);
 	if (!geom_state || geom_bytes < g.total_bytes) return fail(SGR_ENOMEM, "geom_state too small: %zu < %zu", geom_bytes, g.total_bytes);
 	if (!img_state || img_bytes < img.total_bytes) return fail(SGR_ENOMEM, "img_state too small: %zu < %zu", img_bytes, img.total_bytes);
+	if (bounded) {
+		if (capacity > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "capacity %lld exceeds 2^31-1", (long long)capacity);
+		const size_t need = carve_bin(nullptr, capacity).total_bytes;
+		if (capacity > 0 && (!bounded_state || bounded_bytes < need))
+			return fail(SGR_ENOMEM, "binning_state too small for capacity %lld: %zu < %zu", (long long)capacity, bounded_bytes, need);
+	}
 
 	int64_t R = 0;
 	BinView b = carve_bin(nullptr, 0);
@@ -153,14 +195,18 @@ int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, c
 		SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
 		        "preprocess_fwd");
 		SGR_TRY(launch_depth_order(f, g, st), "depth_order");
-		uint32_t r32 = 0;
-		cudaError_t e = cudaMemcpyAsync(&r32, g.offsets + (f.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-		if (e != cudaSuccess) return fail(SGR_ECUDA, "instance count read-back: %s", cudaGetErrorString(e));
-		R = (int64_t)r32;
-		if (R > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "instance count %lld exceeds 2^31-1", (long long)R);
+		if (!bounded) {
+			uint32_t r32 = 0;
+			cudaError_t e = read_back_u32(&r32, g.offsets + (f.P - 1), st);
+			if (e != cudaSuccess) return fail(SGR_ECUDA, "instance count read-back: %s", cudaGetErrorString(e));
+			R = (int64_t)r32;
+			if (R > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "instance count %lld exceeds 2^31-1", (long long)R);
+		}
 	}
-	if (R > 0) {
+	if (bounded) {
+		R = capacity;
+		if (capacity > 0) b = carve_bin(bounded_state, capacity);
+	} else if (R > 0) {
 		if (!alloc) return fail(SGR_EINVAL, "alloc callback is NULL");
 		const size_t need = carve_bin(nullptr, R).total_bytes;
 		void *bin = alloc(alloc_user, need);
@@ -169,8 +215,53 @@ int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, c
 		if (binning_state) *binning_state = bin;
 	}
 	if (num_instances) *num_instances = R;
-	SGR_TRY(launch_binning(f, g, radii, b, img, R, st), "binning");
+	SGR_TRY(launch_binning(f, g, radii, b, img, R, st, bounded ? capacity : -1), "binning");
 	SGR_TRY(launch_blend_fwd(f, g, b, img, semantics, out_color, out_depth, out_alpha, out_semantic, st), "blend_fwd");
+	return SGR_OK;
+}
+
+int sgr_forward(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                const float *semantics, const float *opacities, const float *scales, const float *rotations,
+                const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
+                int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
+                void *alloc_user, void **binning_state, int64_t *num_instances, void *stream) {
+	return forward_impl(frame, means3D, shs, colors_precomp, semantics, opacities, scales, rotations, cov3D_precomp, out_color, out_depth,
+	                    out_alpha, out_semantic, radii, geom_state, geom_bytes, img_state, img_bytes, alloc, alloc_user, binning_state,
+	                    num_instances, nullptr, 0, -1, stream);
+}
+
+int sgr_forward_bounded(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                        const float *semantics, const float *opacities, const float *scales, const float *rotations,
+                        const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
+                        int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes,
+                        void *binning_state, size_t binning_bytes, int64_t capacity, void *stream) {
+	if (capacity < 0) return fail(SGR_EINVAL, "capacity must be >= 0");
+	return forward_impl(frame, means3D, shs, colors_precomp, semantics, opacities, scales, rotations, cov3D_precomp, out_color, out_depth,
+	                    out_alpha, out_semantic, radii, geom_state, geom_bytes, img_state, img_bytes, nullptr, nullptr, nullptr, nullptr,
+	                    binning_state, binning_bytes, capacity, stream);
+}
+
+int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	if (!geom_state || !host_status) return fail(SGR_EINVAL, "NULL pointer passed to sgr_forward_status_async");
+	host_status[0] = host_status[1] = 0;
+	if (f.P == 0) return SGR_OK;
+	const GeomView g = carve_geom(const_cast<void *>(geom_state), f.P);
+	cudaError_t e = cudaMemcpyAsync(host_status, g.big_count + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream));
+	if (e != cudaSuccess) return fail(SGR_ECUDA, "status copy: %s", cudaGetErrorString(e));
+	return SGR_OK;
+}
+
+int sgr_forward_status(const SgrFrame *frame, const void *geom_state, int64_t *num_instances, int32_t *overflowed, void *stream) {
+	uint32_t h[2] = {0, 0};
+	int rc = sgr_forward_status_async(frame, geom_state, h, stream);
+	if (rc) return rc;
+	cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+	if (e != cudaSuccess) return fail(SGR_ECUDA, "status sync: %s", cudaGetErrorString(e));
+	if (num_instances) *num_instances = (int64_t)h[0];
+	if (overflowed) *overflowed = (int32_t)h[1];
 	return SGR_OK;
 }
 

@@ -35,7 +35,8 @@ struct GeomView {
 	uint32_t *perm;           // Gaussian indices in ascending (depth, index) order
 	uint32_t *offsets;        // inclusive scan of tiles_touched[perm[.]]  (depth order)
 	uint32_t *big_list;       // depth-order positions of Gaussians whose rectangle is emitted by a whole warp (emit_big_kernel)
-	uint32_t *big_count;      // number of entries in big_list (device counter, zeroed per forward)
+	uint32_t *big_count;      // [0] number of entries in big_list (device counter, zeroed per forward)
+	                          // [1] instance count R of the last forward, [2] overflow flag, [3] instances actually emitted (bounded mode)
 	void *temp;               // cub temp storage: max(scan, depth sort)
 	size_t temp_bytes;
 	size_t total_bytes;
@@ -149,8 +150,10 @@ cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, 
 cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
 size_t geom_temp_bytes(int P);
 size_t sort_temp_bytes(int64_t R);
+// cap < 0: exact mode, R is the host-known instance count.  cap >= 0: bounded mode, R is ignored, the arrays hold `cap`
+// slots and the true count lives in g.big_count[1..3].
 cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, BinView b, ImgView img, int64_t R,
-                           cudaStream_t st);
+                           cudaStream_t st, int64_t cap = -1);
 cudaError_t launch_blend_fwd(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *semantics, float *out_color,
                              float *out_depth, float *out_alpha, float *out_sem, cudaStream_t st);
 cudaError_t launch_blend_bwd(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *semantics,

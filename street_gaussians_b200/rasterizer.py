@@ -86,8 +86,47 @@ class _ForwardState:
     __slots__ = ("geom", "img", "binning", "num_instances")
 
 
+class InstanceCapacity:
+    """Opt-in, sync-free binning (include/sgr.h: sgr_forward_bounded).  The reference — and this library by default —
+    blocks the host once per forward to read the instance count R back and size the sort buffers.  With a capacity
+    object the buffers are sized from the largest R seen so far (x `headroom`), nothing is read back inside forward, and
+    the true count of each frame arrives asynchronously in pinned memory; `check()` (called at the start of the next
+    forward and from `GaussianRasterizer.synchronize_capacity()`) raises if a frame did not fit, after growing the capacity.
+    The first frame(s) run in exact mode to learn R."""
+
+    def __init__(self, headroom: float = 1.25, initial: Optional[int] = None):
+        self.headroom, self.capacity = float(headroom), (int(initial) if initial else None)
+        self._pending = []  # (pinned uint32[2], cuda event)
+
+    def observe(self, R: int):
+        want = int(R * self.headroom) + 4096
+        if self.capacity is None or want > self.capacity:
+            self.capacity = want
+
+    def track(self, host_status: torch.Tensor, event):
+        self._pending.append((host_status, event))
+
+    def check(self, wait: bool = False):
+        keep = []
+        for host_status, ev in self._pending:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                keep.append((host_status, ev))
+                continue
+            R, overflow = int(host_status[0]), int(host_status[1])
+            if overflow:
+                old = self.capacity
+                self.observe(R)
+                self._pending = keep
+                raise _capi.SgrError(f"instance capacity {old} overflowed (frame needed {R}); capacity raised to {self.capacity} — "
+                                     "re-render that frame")
+            self.observe(R)
+        self._pending = keep
+
+
 def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
-                  settings: GaussianRasterizationSettings, band: Optional[TileRowBand]):
+                  settings: GaussianRasterizationSettings, band: Optional[TileRowBand], capacity: Optional["InstanceCapacity"] = None):
     L = _capi.lib()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # DGR/rasterize_points.cu:58-60
@@ -129,6 +168,30 @@ def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rot
     st.geom = torch.empty((gb.value,), device=device, dtype=torch.uint8)
     st.img = torch.empty((ib.value,), device=device, dtype=torch.uint8)
 
+    if capacity is not None:
+        capacity.check()
+    if capacity is not None and capacity.capacity is not None:
+        # bounded mode: no host synchronisation anywhere in this call
+        cap = int(capacity.capacity)
+        nbytes = int(L.sgr_binning_bytes(cap))
+        st.binning = torch.empty((nbytes,), device=device, dtype=torch.uint8)
+        with torch.cuda.device(device):
+            rc = L.sgr_forward_bounded(C.byref(fr), _ptr(tensors["means3D"]), _ptr(tensors["sh"]), _ptr(tensors["colors_precomp"]),
+                                       _ptr(tensors["semantics"]), _ptr(tensors["opacities"]), _ptr(tensors["scales"]),
+                                       _ptr(tensors["rotations"]), _ptr(tensors["cov3Ds_precomp"]), _ptr(color), _ptr(depth), _ptr(alpha),
+                                       _ptr(semantic), _ptr(radii), _ptr(st.geom), gb.value, _ptr(st.img), ib.value, _ptr(st.binning), nbytes,
+                                       cap, _stream(device))
+            _capi.check(rc, "sgr_forward_bounded")
+            host_status = torch.zeros(2, dtype=torch.int32).pin_memory()
+            rc = L.sgr_forward_status_async(C.byref(fr), _ptr(st.geom), C.c_void_p(host_status.data_ptr()), _stream(device))
+            _capi.check(rc, "sgr_forward_status_async")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+        capacity.track(host_status, ev)
+        st.num_instances = cap
+        del keep
+        return color, radii, depth, alpha, semantic, st, tensors
+
     def _alloc(_user, nbytes):
         st.binning = torch.empty((int(nbytes),), device=device, dtype=torch.uint8)
         return st.binning.data_ptr()
@@ -143,6 +206,8 @@ def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rot
                            C.byref(bin_ptr), C.byref(n_inst), _stream(device))
     _capi.check(rc, "sgr_forward")
     st.num_instances = int(n_inst.value)
+    if capacity is not None:
+        capacity.observe(st.num_instances)
     del keep
     return color, radii, depth, alpha, semantic, st, tensors
 
@@ -196,9 +261,9 @@ def _backward_geom_impl(settings, band, st: _ForwardState, tensors, radii, grad2
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, band=None, grad_reduce=None):
+                raster_settings, band=None, grad_reduce=None, capacity=None):
         color, radii, depth, alpha, semantic, st, tensors = _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales,
-                                                                          rotations, cov3Ds_precomp, raster_settings, band)
+                                                                          rotations, cov3Ds_precomp, raster_settings, band, capacity)
         ctx.raster_settings, ctx.band, ctx.state, ctx.tensors, ctx.grad_reduce = raster_settings, band, st, tensors, grad_reduce
         ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype)
                            for t in (means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp))
@@ -219,7 +284,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             return torch.zeros(shape, device=device, dtype=dtype)
 
         if tensors is None:  # P == 0
-            return tuple(zeros_like_input(i) for i in range(9)) + (None, None, None)
+            return tuple(zeros_like_input(i) for i in range(9)) + (None, None, None, None)
         dev = tensors["means3D"].device
         H, W = int(settings.image_height), int(settings.image_width)
         S = int(tensors["semantics"].shape[1]) if tensors["semantics"] is not None else 0
@@ -243,24 +308,32 @@ class _RasterizeGaussians(torch.autograd.Function):
             return g.reshape(shape).to(device=device, dtype=dtype)
 
         return (fit(g_means3D, 0), fit(g_means2D, 1), fit(g_sh, 2), fit(g_colors, 3), fit(g_sem if S > 0 else None, 4),
-                fit(g_opac, 5), fit(g_scales, 6), fit(g_rots, 7), fit(g_cov, 8), None, None, None)
+                fit(g_opac, 5), fit(g_scales, 6), fit(g_rots, 7), fit(g_cov, 8), None, None, None, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, None, None)
+                                     cov3Ds_precomp, raster_settings, None, None, None)
 
 
 class GaussianRasterizer(nn.Module):
-    """Same surface as the reference class (DGR :181-260).  ``band`` / ``grad_reduce`` are the only additions (keyword-only,
-    default off) and exist for tile-row sharding across GPUs (street_gaussians_b200.sharded)."""
+    """Same surface as the reference class (DGR :181-260).  ``band`` / ``grad_reduce`` (tile-row sharding across GPUs,
+    street_gaussians_b200.sharded) and ``capacity`` (sync-free binning, InstanceCapacity) are the only additions:
+    keyword-only, default off."""
 
-    def __init__(self, raster_settings, *, band: Optional[TileRowBand] = None, grad_reduce=None):
+    def __init__(self, raster_settings, *, band: Optional[TileRowBand] = None, grad_reduce=None,
+                 capacity: Optional[InstanceCapacity] = None):
         super().__init__()
         self.raster_settings = raster_settings
         self.band = band
         self.grad_reduce = grad_reduce
+        self.capacity = capacity  # opt-in sync-free binning; share ONE InstanceCapacity across the rasterizers of a training loop
+
+    def synchronize_capacity(self):
+        """Wait for the outstanding frame statuses of the sync-free mode and raise if any frame overflowed."""
+        if self.capacity is not None:
+            self.capacity.check(wait=True)
 
     def markVisible(self, positions):
         L = _capi.lib()
@@ -296,7 +369,7 @@ class GaussianRasterizer(nn.Module):
         if semantics is None:
             semantics = torch.zeros(means3D.shape[0], 0, dtype=torch.float32, device=means3D.device)
         return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, semantics, opacities, scales, rotations,
-                                         cov3D_precomp, raster_settings, self.band, self.grad_reduce)
+                                         cov3D_precomp, raster_settings, self.band, self.grad_reduce, self.capacity)
 
     def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None) -> Tuple[torch.Tensor, torch.Tensor]:
         L = _capi.lib()

@@ -36,7 +36,7 @@ class ShardedGaussianRasterizer(GaussianRasterizer):
     screen-space sums.  With world == 1 it is exactly GaussianRasterizer."""
 
     def __init__(self, raster_settings: GaussianRasterizationSettings, group: Optional[dist.ProcessGroup] = None,
-                 layout: str = "cyclic"):
+                 layout: str = "cyclic", capacity=None):
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
         band = None
@@ -51,7 +51,7 @@ class ShardedGaussianRasterizer(GaussianRasterizer):
                     dist.all_reduce(g_sem, op=dist.ReduceOp.SUM, group=group)
                 return grad2d, g_sem
 
-        super().__init__(raster_settings, band=band, grad_reduce=reduce)
+        super().__init__(raster_settings, band=band, grad_reduce=reduce, capacity=capacity)
         self.group, self.world, self.rank = group, world, rank
 
     def gather_images(self, *images: torch.Tensor):

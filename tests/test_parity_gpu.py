@@ -343,3 +343,30 @@ def test_direct_c_abi_error_paths():
     fr.S = 33
     rc = L.sgr_backward_blend(C.byref(fr), 0, vp(m), vp(buf), None, vp(buf), vp(one), vp(img), vp(one), vp(one), vp(img), vp(buf), vp(buf), None)
     assert rc == -4
+
+
+def test_bounded_sync_free_mode():
+    """sgr_forward_bounded (no host read-back): identical images/gradients to the exact mode when the capacity suffices;
+    overflow is detected, reported and recoverable."""
+    scene = synthetic.make_scene(P=40_000, width=640, height=416, sh_degree=3, seed=81, pose=True)
+    exact = util.run_api(sgb, scene)
+    cap = sgb.InstanceCapacity(headroom=1.3)
+    first = util.run_api(sgb, scene, rasterizer_kwargs=dict(capacity=cap))      # exact mode, learns R
+    assert cap.capacity is not None and cap.capacity > 0
+    bounded = util.run_api(sgb, scene, rasterizer_kwargs=dict(capacity=cap))    # bounded mode
+    cap.check(wait=True)
+    for k in ("color", "depth", "alpha", "radii"):
+        assert (bounded[k] == exact[k]).all() and (first[k] == exact[k]).all(), k
+    for k in exact:
+        if k.startswith("g_") and exact[k] is not None:
+            assert util.rel_err(bounded[k], exact[k]) < 1e-5, k
+    # a capacity that is far too small: the frame is truncated, the status says so, the capacity grows, the retry is exact
+    small = sgb.InstanceCapacity(initial=2000)
+    truncated = util.run_api(sgb, scene, backward=False, rasterizer_kwargs=dict(capacity=small))
+    assert np.isfinite(truncated["color"]).all()
+    with pytest.raises(_capi.SgrError, match="overflowed"):
+        small.check(wait=True)
+    assert small.capacity > 2000
+    retry = util.run_api(sgb, scene, backward=False, rasterizer_kwargs=dict(capacity=small))
+    small.check(wait=True)
+    assert (retry["color"] == exact["color"]).all()
