@@ -141,7 +141,12 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 					valid = !(alpha < 1.0f / 255.0f);
 					if (valid) {
 						const float4 q2 = ld4(a + 32);  // r, g, b, clamp bits
-						const float inv = 1.0f / (1.f - alpha);  // one IEEE division serves T/(1-a) and T_final/(1-a)
+						// 1/(1-alpha), alpha <= 0.99: hardware reciprocal + one Newton step (<= 1 ulp) = 3 instructions instead of
+						// the ~8 of an IEEE division with its special-case path; serves both T/(1-a) and T_final/(1-a)
+						const float oma = 1.f - alpha;  // in [0.01, 1]: no special cases to guard
+						float r0;
+						asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(oma));
+						const float inv = fmaf(r0, fmaf(-oma, r0, 1.0f), r0);
 						T = T * inv;
 						w = alpha * T;
 						// The reference keeps one "value behind" accumulator per blended quantity (3 colours, depth, the constant 1
