@@ -98,13 +98,20 @@ static int check(cudaError_t e, const char *what, bool debug, cudaStream_t st) {
 // BLOCKING wait on an event (the thread sleeps instead of spinning in cudaStreamSynchronize).  With one process per GPU
 // on a box whose container has fewer host cores than 2 x GPUs (this pool: cgroup quota of 16 cores for 8 GPUs) eight
 // spinning main threads plus eight autograd threads exhaust the quota and every rank gets throttled — measured as the
-// N=8 step time being 1.5 ms above the sum of its stages (profiles/r01_summary.md §5).  SGR_SYNC_MODE=spin restores the
-// lower-latency busy wait for single-GPU use.
+// N=8 step time being 1.5 ms above the sum of its stages (profiles/r01_summary.md §5).
 static cudaError_t read_back_u32(uint32_t *dst, const uint32_t *src_dev, cudaStream_t st) {
 	static thread_local uint32_t *pinned = nullptr;
 	static thread_local cudaEvent_t ev = nullptr;
 	static thread_local int ev_dev = -1;
-	static const bool spin = [] { const char *m = getenv("SGR_SYNC_MODE"); return m && strcmp(m, "spin") == 0; }();
+	// policy: SGR_SYNC_MODE=spin|block wins; otherwise spin when this is the only rank on the node (2 % faster at N=1:
+	// 1.91 vs 1.95 ms/step on config C) and sleep when torchrun-style launchers announce several local ranks
+	static const bool spin = [] {
+		const char *m = getenv("SGR_SYNC_MODE");
+		if (m) return strcmp(m, "spin") == 0;
+		const char *w = getenv("LOCAL_WORLD_SIZE");
+		if (!w) w = getenv("WORLD_SIZE");
+		return !(w && atoi(w) > 1);
+	}();
 	cudaError_t e;
 	if (!pinned && (e = cudaHostAlloc(reinterpret_cast<void **>(&pinned), 64, cudaHostAllocDefault)) != cudaSuccess) return e;
 	int dev = 0;
