@@ -81,6 +81,14 @@ def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _dump(path: str, args) -> None:
+    """CPU deep copy of the call's arguments, written with torch.save — the reference's debug post-mortem."""
+    try:
+        torch.save(tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args), path)
+    except Exception:
+        pass
+
+
 class _ForwardState:
     """Caller-owned forward->backward state (the reference keeps geomBuffer/binningBuffer/imgBuffer byte tensors)."""
     __slots__ = ("geom", "img", "binning", "num_instances")
@@ -262,8 +270,18 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings, band=None, grad_reduce=None, capacity=None):
-        color, radii, depth, alpha, semantic, st, tensors = _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales,
-                                                                          rotations, cov3Ds_precomp, raster_settings, band, capacity)
+        try:
+            color, radii, depth, alpha, semantic, st, tensors = _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales,
+                                                                              rotations, cov3Ds_precomp, raster_settings, band, capacity)
+        except Exception:
+            if raster_settings.debug:  # same post-mortem as the reference (DGR/diff_gaussian_rasterization/__init__.py:87-94)
+                _dump("snapshot_fw.dump", (raster_settings.bg, means3D, colors_precomp, semantics, opacities, scales, rotations,
+                                           raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
+                                           raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy,
+                                           raster_settings.image_height, raster_settings.image_width, sh, raster_settings.sh_degree,
+                                           raster_settings.campos, raster_settings.prefiltered, raster_settings.debug))
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            raise
         ctx.raster_settings, ctx.band, ctx.state, ctx.tensors, ctx.grad_reduce = raster_settings, band, st, tensors, grad_reduce
         ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype)
                            for t in (means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp))
@@ -293,10 +311,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_depth = grad_depth if grad_depth is not None else zimg(1)
         grad_alpha = grad_alpha if grad_alpha is not None else zimg(1)
         grad_semantic = grad_semantic if grad_semantic is not None else zimg(S)
-        grad2d, g_sem = _backward_blend_impl(settings, band, st, tensors, alpha, grad_color, grad_depth, grad_alpha, grad_semantic)
-        if ctx.grad_reduce is not None:  # multi-GPU: sum the per-band partial sums across ranks (one collective)
-            grad2d, g_sem = ctx.grad_reduce(grad2d, g_sem)
-        g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov = _backward_geom_impl(settings, band, st, tensors, radii, grad2d)
+        try:
+            grad2d, g_sem = _backward_blend_impl(settings, band, st, tensors, alpha, grad_color, grad_depth, grad_alpha, grad_semantic)
+            if ctx.grad_reduce is not None:  # multi-GPU: sum the per-band partial sums across ranks (one collective)
+                grad2d, g_sem = ctx.grad_reduce(grad2d, g_sem)
+            g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov = _backward_geom_impl(settings, band, st, tensors, radii, grad2d)
+        except Exception:
+            if settings.debug:  # DGR/diff_gaussian_rasterization/__init__.py:141-148
+                _dump("snapshot_bw.dump", (settings.bg, tensors["means3D"], radii, tensors["colors_precomp"], tensors["scales"],
+                                           tensors["rotations"], settings.scale_modifier, tensors["cov3Ds_precomp"], settings.viewmatrix,
+                                           settings.projmatrix, settings.tanfovx, settings.tanfovy, grad_color, grad_depth, grad_alpha,
+                                           grad_semantic, tensors["sh"], settings.sh_degree, settings.campos, alpha, tensors["semantics"],
+                                           settings.debug))
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+            raise
 
         def fit(g, i):
             """cast/reshape a gradient to the original input's shape, dtype and device (None stays None)."""

@@ -134,3 +134,25 @@ def test_band_helpers():
     b = cyclic_band(100, 3, 8)  # 7 tile rows, rank 3 owns row 3 only
     assert (b.begin, b.end, b.step) == (3, 7, 8)
     assert cyclic_band(16, 5, 8).end == 0  # more ranks than rows -> empty band
+
+
+def test_debug_mode_dumps_inputs_like_the_reference(tmp_path, monkeypatch):
+    """debug=True: a failing forward leaves snapshot_fw.dump with the 20 arguments of the reference's
+    _C.rasterize_gaussians call (DGR/diff_gaussian_rasterization/__init__.py:87-94)."""
+    monkeypatch.chdir(tmp_path)
+    st = _settings()._replace(debug=True)
+    r = sgb.GaussianRasterizer(st)
+    with pytest.raises(_capi.SgrError):
+        r(torch.zeros(4, 3), None, torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    dump = torch.load(tmp_path / "snapshot_fw.dump")
+    assert len(dump) == 20 and dump[1].shape == (4, 3) and dump[-1] is True
+
+
+def test_instance_capacity_bookkeeping():
+    cap = sgb.InstanceCapacity(headroom=1.5)
+    assert cap.capacity is None
+    cap.observe(1000)
+    assert cap.capacity == 1500 + 4096
+    cap.observe(10)          # never shrinks
+    assert cap.capacity == 1500 + 4096
+    cap.check()              # nothing pending: no-op
