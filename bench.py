@@ -344,10 +344,14 @@ def main():
         alg_bytes = n_inst * 44 + npx * rows_frac * 28 + visible * 44
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (stages["blend_bwd"] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of blend_bwd2_kernel from the committed `ncu --set full` capture
+        # (profiles/r01_ncu_full.md: 72.97 MB + 3.53 MB); only valid for the workload/size it was captured on
+        traffic = 76.5e6 if (args.workload == "C" and not use_dist) else None
         roofline = dict(bound="hbm", kernel="blend_bwd2_kernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                        traffic=None, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
-                        note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d); the HBM fraction is reported as the "
-                             "contract asks; kernel_ms includes two cudaMemsetAsync of the accumulators")
+                        traffic=traffic, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
+                        note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d; ncu: 76 % issue-active, 1.4 % DRAM): "
+                             "real DRAM traffic is 8x BELOW the algorithmic bytes because the tile lists and records are L2 hits; the HBM "
+                             "fraction is reported as the contract asks; kernel_ms includes the cudaMemsetAsync of the accumulators")
 
     # ---- end to end from pinned host memory ----
     if args.no_e2e:
@@ -426,7 +430,7 @@ def main():
                                 exact_mode_ms_per_step=exact_ms),
                     e2e=dict(value=1000.0 / e2e_ms, unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                              note="pinned host -> device copy of all 59 floats/Gaussian every step, double-buffered on a copy stream; scalar loss read back"),
-                    gpu_launches=(20 * args.steps) if not ref_cuda else 0, clocks=clocks)
+                    gpu_launches=((21 if args.sync_free else 20) * args.steps) if not ref_cuda else 0, clocks=clocks)
         if roofline:
             line["roofline"] = roofline
         if cb:

@@ -61,8 +61,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 			const float4 *src = reinterpret_cast<const float4 *>(shs + g0 * nsh);
 			const int n4 = rows * nsh / 4;
 			for (int e = lane; e < n4; e += 32) {
-				// (runtime integer division costs ~20 instructions; M = 16 is the shipped configuration)
-				const int row = nsh == 48 ? e / 12 : (4 * e) / nsh, col = (4 * e) - row * nsh;
+				const int row = (4 * e) / nsh, col = (4 * e) - row * nsh;
 				if ((vis_mask >> row) & 1u) {
 					const float4 v = __ldg(src + e);
 					float *d = wbase + row * kShRow + col;
@@ -322,7 +321,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 			float4 *dst = reinterpret_cast<float4 *>(dL_dsh + g0s * nsh);
 			const int n4 = rows * nsh / 4;
 			for (int e = lane; e < n4; e += 32) {
-				const int row = nsh == 48 ? e / 12 : (4 * e) / nsh, col = (4 * e) - row * nsh;
+				const int row = (4 * e) / nsh, col = (4 * e) - row * nsh;
 				const float *sp = wbase + row * kShRow + col;
 				dst[e] = make_float4(sp[0], sp[1], sp[2], sp[3]);
 			}
