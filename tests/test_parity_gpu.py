@@ -401,3 +401,47 @@ def test_config_E_forward_band_union_and_determinism():
     for k in ("color", "depth", "alpha"):
         assert (sum(p[k] for p in parts) == a[k]).all(), k
     assert np.isfinite(a["color"]).all() and a["alpha"].max() <= 1.0 + 1e-5
+
+
+def test_bounded_mode_with_tile_row_band():
+    """sync-free binning composed with tile-row sharding (what bench.py --gpus N runs): band results identical to the exact mode."""
+    from street_gaussians_b200.sharded import cyclic_band
+    scene = synthetic.make_scene(P=60_000, width=800, height=608, sh_degree=2, seed=91, pose=True, scale_med=0.02)
+    band = cyclic_band(608, 1, 3)
+    exact = util.run_api(sgb, scene, rasterizer_kwargs=dict(band=band))
+    cap = sgb.InstanceCapacity()
+    util.run_api(sgb, scene, backward=False, rasterizer_kwargs=dict(band=band, capacity=cap))  # learns R
+    bounded = util.run_api(sgb, scene, rasterizer_kwargs=dict(band=band, capacity=cap))
+    cap.check(wait=True)
+    for k in ("color", "depth", "alpha", "radii"):
+        assert (bounded[k] == exact[k]).all(), k
+    for k in exact:
+        if k.startswith("g_") and exact[k] is not None:
+            assert util.rel_err(bounded[k], exact[k]) < 1e-5, k
+
+
+def test_more_than_65536_tiles_uses_32bit_tile_ids():
+    """4112 x 4112 px = 257 x 257 = 66,049 tiles: the u32-key paths of emit / sort / ranges (exact and bounded)."""
+    scene = synthetic.make_scene(P=3000, width=4112, height=4112, sh_degree=1, seed=92, pose=True, scale_med=0.05)
+    exact = util.run_api(sgb, scene, backward=False)
+    orc = util.run_oracle(scene, backward=False)
+    orc.pop("_fw")
+    assert_forward_close(exact, orc, 4112 * 4112, allow_flips=flips_allowed(4112 * 4112))
+    cap = sgb.InstanceCapacity()
+    util.run_api(sgb, scene, backward=False, rasterizer_kwargs=dict(capacity=cap))
+    bounded = util.run_api(sgb, scene, backward=False, rasterizer_kwargs=dict(capacity=cap))
+    cap.check(wait=True)
+    for k in ("color", "depth", "alpha"):
+        assert (bounded[k] == exact[k]).all(), k
+
+
+def test_forward_with_more_than_32_feature_channels():
+    """Forward accepts any S (channel chunks of 32); backward is capped at SGR_MAX_SEMANTIC_BWD and says so."""
+    scene = synthetic.make_scene(P=1500, width=128, height=96, sh_degree=0, seed=93, pose=True, scale_med=0.06, semantics=40)
+    mine = util.run_api(sgb, scene, backward=False)
+    orc = util.run_oracle(scene, backward=False)
+    orc.pop("_fw")
+    assert mine["semantic"].shape == (40, 96, 128)
+    assert_forward_close(mine, orc, 128 * 96, allow_flips=flips_allowed(128 * 96))
+    with pytest.raises(_capi.SgrError, match="at most 32 semantic channels"):
+        util.run_api(sgb, scene, backward=True)
