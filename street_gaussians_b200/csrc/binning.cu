@@ -121,22 +121,40 @@ __global__ void __launch_bounds__(256) emit_big_kernel(const FrameDev f, const G
 
 // One thread per sorted instance: a tile's range starts / ends where the tile id changes
 // (reference identifyTileRanges, rasterizer_impl.cu:116-138).  ranges must be zero-initialised.
+constexpr int kRangeKeysPerThread = 8;
 template <typename KeyT>
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const KeyT *__restrict__ keys, uint2 *__restrict__ ranges, const uint32_t ntile) {
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= L) return;
-	// keys >= ntile are the padding of the bounded mode (they sort behind every real tile)
-	const uint32_t cur = keys[idx];
-	if (idx == 0) {
-		if (cur < ntile) ranges[cur].x = 0;
+	// 8 consecutive keys per thread (one 16-B load for 16-bit tile ids): the one-key-per-thread version ran at 0.6 TB/s.
+	const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRangeKeysPerThread;
+	if (base >= L) return;
+	uint32_t k[kRangeKeysPerThread];
+	if (base + kRangeKeysPerThread <= L) {
+		if (sizeof(KeyT) == 2) {
+			const uint4 v = *reinterpret_cast<const uint4 *>(keys + base);  // base is a multiple of 8 -> 16-B aligned
+			k[0] = v.x & 0xffffu; k[1] = v.x >> 16; k[2] = v.y & 0xffffu; k[3] = v.y >> 16;
+			k[4] = v.z & 0xffffu; k[5] = v.z >> 16; k[6] = v.w & 0xffffu; k[7] = v.w >> 16;
+		} else {
+			const uint4 a = reinterpret_cast<const uint4 *>(keys + base)[0], b = reinterpret_cast<const uint4 *>(keys + base)[1];
+			k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+		}
 	} else {
-		const uint32_t prev = keys[idx - 1];
-		if (cur != prev) {
-			if (prev < ntile) ranges[prev].y = (uint32_t)idx;
+#pragma unroll
+		for (int i = 0; i < kRangeKeysPerThread; i++) k[i] = base + i < L ? (uint32_t)keys[base + i] : 0xffffffffu;
+	}
+	// keys >= ntile are the padding of the bounded mode (they sort behind every real tile)
+	uint32_t prev = base == 0 ? 0xffffffffu : (uint32_t)keys[base - 1];
+#pragma unroll
+	for (int i = 0; i < kRangeKeysPerThread; i++) {
+		const int64_t idx = base + i;
+		if (idx >= L) break;
+		const uint32_t cur = k[i];
+		if (cur != prev || idx == 0) {
+			if (idx != 0 && prev < ntile) ranges[prev].y = (uint32_t)idx;
 			if (cur < ntile) ranges[cur].x = (uint32_t)idx;
 		}
+		if (idx == L - 1 && cur < ntile) ranges[cur].y = (uint32_t)L;
+		prev = cur;
 	}
-	if (idx == L - 1 && cur < ntile) ranges[cur].y = (uint32_t)L;
 }
 
 // status words: [1] = R (true instance count), [2] = overflow flag, [3] = instances actually emitted (<= cap)
@@ -197,7 +215,7 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, kin, kout, b.vals_in, b.vals_out, R, 0, sort_bits, st);
 		if (e != cudaSuccess) return e;
-		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, kout, img.ranges, (uint32_t)ntile);
+		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 256 * kRangeKeysPerThread - 1) / (256 * kRangeKeysPerThread)), 256, 0, st>>>(R, kout, img.ranges, (uint32_t)ntile);
 	} else {
 		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
 		emit_big_kernel<uint32_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
@@ -205,7 +223,7 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, R, 0, sort_bits, st);
 		if (e != cudaSuccess) return e;
-		tile_ranges_kernel<uint32_t><<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, b.keys_out, img.ranges, (uint32_t)ntile);
+		tile_ranges_kernel<uint32_t><<<(unsigned)((R + 256 * kRangeKeysPerThread - 1) / (256 * kRangeKeysPerThread)), 256, 0, st>>>(R, b.keys_out, img.ranges, (uint32_t)ntile);
 	}
 	return cudaGetLastError();
 }
