@@ -53,6 +53,10 @@ def parse():
                          "this is the default for the timed region; the exact drop-in mode is timed beside it "
                          "(config.exact_mode_ms_per_step)")
     ap.add_argument("--exact", dest="sync_free", action="store_false", help="force the exact (read-back) mode")
+    ap.add_argument("--mp-mode", choices=["gaussian", "replicated"], default="gaussian",
+                    help="N > 1 only. gaussian: every rank owns P/N Gaussians and a tile-row band (all-gather of records, "
+                         "reduce-scatter of grad2d; GaussianShardedRasterizer).  replicated: parameters replicated, tile rows "
+                         "sharded, one all-reduce (ShardedGaussianRasterizer)")
     ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--diag", action="store_true", help="per-rank host/all-reduce timing breakdown on stderr")
     ap.add_argument("--cpu-sample-stride", type=int, default=0, help="CPU baseline uses every k-th Gaussian (0 = auto)")
@@ -226,10 +230,18 @@ def main():
             # what the UNCHANGED reference call site gets — is timed right after and reported as exact_mode_ms_per_step.
             args.sync_free = True
         capacity = mod.InstanceCapacity() if args.sync_free else None
-        rast = ShardedGaussianRasterizer(make_settings(mod, cam, dev), capacity=capacity)
+        if use_dist and args.mp_mode == "gaussian":
+            from street_gaussians_b200.sharded import GaussianShardedRasterizer
+            chunk = (P + world - 1) // world
+            rast = GaussianShardedRasterizer(make_settings(mod, cam, dev), capacity=capacity, chunk=chunk)
+        else:
+            rast = ShardedGaussianRasterizer(make_settings(mod, cam, dev), capacity=capacity)
 
-    params = {k: scene[k].to(dev).requires_grad_(True) for k in PARAM_KEYS}
-    means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+    gauss_sharded = use_dist and args.mp_mode == "gaussian" and not ref_cuda
+    lo, hi = (min(P, rank * chunk), min(P, (rank + 1) * chunk)) if gauss_sharded else (0, P)
+    local_scene = {k: scene[k][lo:hi].contiguous() for k in PARAM_KEYS}  # this rank's Gaussians (all of them unless Gaussian-sharded)
+    params = {k: local_scene[k].to(dev).requires_grad_(True) for k in PARAM_KEYS}
+    means2D = torch.zeros((hi - lo, 3), device=dev, requires_grad=True)
     gc, gd, ga = (scene[k].to(dev) for k in ("grad_color", "grad_depth", "grad_alpha"))
     if use_dist:  # band-local loss: upstream grads are only defined on this rank's rows
         from street_gaussians_b200.sharded import band_of_rows
@@ -253,7 +265,7 @@ def main():
     # ---- device-resident throughput ----
     sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clock_sampler) else None
     diag = {"ar": [], "host": []}
-    if args.diag and use_dist and rast.grad_reduce is not None:
+    if args.diag and use_dist and getattr(rast, "grad_reduce", None) is not None:
         inner = rast.grad_reduce
 
         def timed_reduce(g2d, gsem):
@@ -290,7 +302,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    visible = int((radii > 0).sum().item())
+    vis_t = (radii > 0).sum()
+    if gauss_sharded:
+        dist.all_reduce(vis_t, op=dist.ReduceOp.SUM)
+    visible = int(vis_t.item())
     exact_ms = None
     if not ref_cuda and args.sync_free and not use_dist:
         rast_exact = mod.GaussianRasterizer(make_settings(mod, cam, dev))
@@ -315,7 +330,40 @@ def main():
 
     # ---- per-stage device times (CUDA events around the staged C-ABI calls) + roofline of the dominant kernel ----
     roofline, stages, n_inst = None, {}, None
-    if not ref_cuda:
+    if gauss_sharded:
+        from street_gaussians_b200 import sharded as SH
+        st_obj = make_settings(mod, cam, dev)
+        band = rast.band
+        with torch.no_grad():
+            lt = SH._local_tensors(params["means3D"], params["shs"], None, None, params["opacities"], params["scales"], params["rotations"], None)
+            names = ("project", "all_gather", "forward_records", "blend_bwd", "reduce_scatter", "preprocess_bwd")
+            acc = {k: [] for k in names}
+            for it in range(3 + 5):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+                evs[0].record()
+                rec, radii_l = SH.project_records(lt, st_obj, chunk)
+                evs[1].record()
+                fs, rec_all, gb, ib = SH.alloc_gathered(st_obj, chunk * world, 0, dev)
+                radii_all = torch.empty((chunk * world,), device=dev, dtype=torch.int32)
+                dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1))
+                dist.all_gather_into_tensor(radii_all, radii_l)
+                evs[2].record()
+                col, dep, alp, sem = SH.forward_records(st_obj, band, fs, (gb, ib), radii_all, None)
+                evs[3].record()
+                g2d, gsem = SH.backward_blend_records(st_obj, band, fs, chunk * world, None, alp, gc, gd, ga, None)
+                evs[4].record()
+                g2l = torch.empty((chunk, 12), device=dev)
+                dist.reduce_scatter_tensor(g2l.view(-1), g2d.view(-1))
+                evs[5].record()
+                SH.backward_geom_local(st_obj, lt, rec, radii_l, g2l)
+                evs[6].record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    for i, k in enumerate(names):
+                        acc[k].append(evs[i].elapsed_time(evs[i + 1]))
+            stages = {k: float(np.median(v)) for k, v in acc.items()}
+            n_inst = int(fs.num_instances)
+    elif not ref_cuda:
         from street_gaussians_b200 import rasterizer as R
         st_obj = make_settings(mod, cam, dev)
         band = rast.band
@@ -338,6 +386,7 @@ def main():
                     acc["forward"].append(a.elapsed_time(b)); acc["blend_bwd"].append(b.elapsed_time(c)); acc["preprocess_bwd"].append(c.elapsed_time(d))
             stages = {k: float(np.median(v)) for k, v in acc.items()}
             n_inst = int(fst.num_instances)
+    if not ref_cuda:
         npx = W * H
         # blend_bwd = R*44 + Npx*28 + V*44 bytes (R = this library's instance count, this rank's band)
         rows_frac = 1.0 / world if use_dist else 1.0
@@ -366,8 +415,8 @@ def main():
         if use_dist:
             dist.destroy_process_group()
         return 0
-    host = {k: scene[k].pin_memory() for k in PARAM_KEYS}
-    h2d_bytes = sum(v.numel() * 4 for v in host.values())
+    host = {k: local_scene[k].pin_memory() for k in PARAM_KEYS}
+    h2d_bytes = sum(v.numel() * 4 for v in host.values())  # this rank's share; summed over ranks below when Gaussian-sharded
     copy_stream = torch.cuda.Stream(device=dev)
     bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -412,6 +461,10 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    if gauss_sharded:
+        t = torch.tensor([float(h2d_bytes)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_bytes = int(t.item())
     if sampler:
         sampler.mark(1)
     clocks = sampler.stop() if sampler else None
@@ -424,13 +477,17 @@ def main():
                     dtype="f32", data="synthetic (seeded; street_gaussians_b200/synthetic.py)",
                     config=dict(workload=wl_desc, P=P, visible=visible, width=W, height=H, sh_degree=cam["sh_degree"],
                                 l2="inputs (%.0f MB of Gaussian parameters) exceed the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6),
-                                parallelism=("tile-row sharded x%d (cyclic rows), 1 NCCL all-reduce of grad2d[P,12]/step" % world) if use_dist else "single GPU",
+                                parallelism=(("Gaussian-sharded x%d (P/N Gaussians + cyclic tile rows per rank): NCCL all-gather of 48-B records, "
+                                              "reduce-scatter of grad2d[P,12]; parameters and gradients stay sharded" % world) if gauss_sharded else
+                                             ("tile-row sharded x%d (cyclic rows), parameters replicated, 1 NCCL all-reduce of grad2d[P,12]/step" % world))
+                                if use_dist else "single GPU",
                                 num_instances=n_inst, gaussians_pixels_per_s=P * W * H * fps, stage_ms=stages,
                                 binning_mode="sync-free (InstanceCapacity)" if args.sync_free else "exact (drop-in default: one 4-byte read-back per forward)",
                                 exact_mode_ms_per_step=exact_ms),
                     e2e=dict(value=1000.0 / e2e_ms, unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
-                             note="pinned host -> device copy of all 59 floats/Gaussian every step, double-buffered on a copy stream; scalar loss read back"),
-                    gpu_launches=((21 if args.sync_free else 20) * args.steps) if not ref_cuda else 0, clocks=clocks)
+                             note="pinned host -> device copy of all 59 floats/Gaussian every step (each rank uploads the Gaussians it owns), double-buffered on a copy stream; scalar loss read back"),
+                    gpu_launches=(((21 if args.sync_free else 20) + (1 if gauss_sharded else 0)) * args.steps) if not ref_cuda else 0,
+                    clocks=clocks)
         if roofline:
             line["roofline"] = roofline
         if cb:

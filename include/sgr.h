@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGR_ABI_VERSION 2
+#define SGR_ABI_VERSION 3
 
 #define SGR_OK 0
 #define SGR_EINVAL (-1)   /* bad argument combination / shape                     */
@@ -150,6 +150,33 @@ int sgr_backward(const SgrFrame *frame, int64_t num_instances, const float *mean
                  const float *dL_dalpha, const float *dL_dsemantic, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh,
                  float *dL_dcolors_precomp, float *dL_dsemantics, float *dL_dopacity, float *dL_dscales,
                  float *dL_drotations, float *dL_dcov3D, float *grad2d_scratch, void *stream);
+
+/* ---- Gaussian-sharded rendering (multi-GPU; no reference counterpart — the reference is single-GPU.  SURVEY.md §8e
+ * "variant A": every rank owns P/N Gaussians AND a tile-row band) --------------------------------------------------
+ * The forward of DGR/cuda_rasterizer/rasterizer_impl.cu:197-343 is split at the point where the per-Gaussian work
+ * (FORWARD::preprocess, forward.cu:155-256) hands fixed-size screen-space records to the per-tile work:
+ *   1. sgr_project          on the rank's own Gaussians -> records[P_local] (sgr_record_bytes() each) + radii[P_local]
+ *   2. caller all-gathers records and radii (NCCL) into the first P_total*sgr_record_bytes() bytes of a geom_state
+ *      sized for P_total, and a radii[P_total] array; padding slots must carry radii == 0
+ *   3. sgr_forward_records  bins / sorts / blends the rank's tile-row band from the gathered records
+ *   4. sgr_backward_blend   (frame.P = P_total) -> partial grad2d[P_total,12]; caller reduce-scatters it
+ *   5. sgr_backward_geom    with frame.P = P_local, geom_state = the rank's own records, grad2d = its reduced slice.
+ * Results are bit-identical to the single-GPU path for the forward images and agree to float summation order in the
+ * gradients (tests/test_parity_gpu.py::test_gaussian_sharded_*). */
+size_t sgr_record_bytes(void);
+/* Step 1.  frame.P = number of local Gaussians; the tile-row band of `frame` is ignored.  Same input rules as
+ * sgr_forward.  Writes records[P] (only slots with radii > 0 are meaningful) and radii[P] (all). */
+int sgr_project(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp,
+                const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp,
+                int32_t *radii, void *records, void *stream);
+/* Step 3.  frame.P = P_total.  geom_state (sgr_state_sizes for P_total) must already hold the gathered records in its
+ * first P_total*sgr_record_bytes() bytes; radii[P_total] is read, never written.  semantics[P_total,S] when S > 0.
+ * capacity < 0: exact mode (instance count read back, binning state through `alloc`, like sgr_forward);
+ * capacity >= 0: bounded mode (caller's binning_state of sgr_binning_bytes(capacity), like sgr_forward_bounded). */
+int sgr_forward_records(const SgrFrame *frame, const int32_t *radii, const float *semantics, float *out_color,
+                        float *out_depth, float *out_alpha, float *out_semantic, void *geom_state, size_t geom_bytes,
+                        void *img_state, size_t img_bytes, sgr_alloc_fn alloc, void *alloc_user, void **binning_state_out,
+                        int64_t *num_instances, void *binning_state, size_t binning_bytes, int64_t capacity, void *stream);
 
 /* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
  * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */

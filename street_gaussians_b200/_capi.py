@@ -8,12 +8,12 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsgr.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_state_sizes", "sgr_binning_bytes", "sgr_forward", "sgr_forward_bounded",
            "sgr_forward_status", "sgr_forward_status_async", "sgr_backward_blend",
            "sgr_backward_geom", "sgr_backward", "sgr_mark_visible", "sgr_visible_filter", "sgr_knn_scratch_bytes",
-           "sgr_knn_mean_dist2"]
+           "sgr_knn_mean_dist2", "sgr_record_bytes", "sgr_project", "sgr_forward_records"]
 
 
 class SgrFrame(C.Structure):
@@ -62,6 +62,14 @@ def lib():
     L.sgr_forward_status.argtypes = [C.POINTER(SgrFrame), vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), vp]
     L.sgr_forward_status_async.restype = C.c_int
     L.sgr_forward_status_async.argtypes = [C.POINTER(SgrFrame), vp, vp, vp]
+    L.sgr_record_bytes.restype = C.c_size_t
+    L.sgr_record_bytes.argtypes = []
+    L.sgr_project.restype = C.c_int
+    L.sgr_project.argtypes = [C.POINTER(SgrFrame)] + [vp] * 7 + [vp, vp, vp]
+    L.sgr_forward_records.restype = C.c_int
+    L.sgr_forward_records.argtypes = [C.POINTER(SgrFrame), vp, vp] + [vp] * 4 + [vp, C.c_size_t, vp, C.c_size_t, ALLOC_FN, vp,
+                                                                                  C.POINTER(vp), C.POINTER(C.c_int64), vp, C.c_size_t,
+                                                                                  C.c_int64, vp]
     L.sgr_backward_blend.restype = C.c_int
     L.sgr_backward_blend.argtypes = [C.POINTER(SgrFrame), C.c_int64] + [vp] * 12
     L.sgr_backward_geom.restype = C.c_int

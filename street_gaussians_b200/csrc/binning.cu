@@ -42,6 +42,43 @@ size_t sort_temp_bytes(int64_t R) {
 	return a > b ? a : b;
 }
 
+// Gaussian-sharded mode (include/sgr.h, sgr_forward_records): the records were projected on other ranks and gathered, so
+// the tail of preprocess_fwd_kernel — instance count against THIS rank's tile-row band, depth sort key, identity
+// permutation — runs here from the 48-B record + radius.  Same tile_rect / make_cull / visit_tiles as the emission
+// kernels below, so counts and emitted ranges agree by construction.
+__global__ void __launch_bounds__(256) count_tiles_kernel(const FrameDev f, const GaussRec *__restrict__ rec,
+                                                         const int32_t *__restrict__ radii, uint32_t *__restrict__ tiles_touched,
+                                                         uint32_t *__restrict__ depth_key, uint32_t *__restrict__ iota) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in_range = idx < f.P;
+	bool ok = false;
+	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+	CullParams cp = {};
+	float depth = 0.f;
+	if (in_range) {
+		const int r = radii[idx];
+		if (r > 0) {
+			const float4 q0 = rec[idx].q0, q1 = rec[idx].q1;
+			tile_rect(q0.x, q0.y, r, f.gx, f.gy, x0, y0, x1, y1);
+			cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+			depth = q1.w;
+			ok = true;
+		}
+	}
+	uint32_t count = 0;
+	visit_tiles<false, uint32_t>(ok, x0, y0, x1, y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
+	if (in_range) {
+		tiles_touched[idx] = count;
+		depth_key[idx] = count > 0 ? __float_as_uint(depth) : 0xffffffffu;
+		iota[idx] = (uint32_t)idx;
+	}
+}
+cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	count_tiles_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.depth_key, g.iota);
+	return cudaGetLastError();
+}
+
 // depth order of the Gaussians + inclusive scan of their instance counts in that order
 cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;

@@ -165,7 +165,7 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
                         const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
                         int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
                         void *alloc_user, void **binning_state, int64_t *num_instances, void *bounded_state, size_t bounded_bytes,
-                        int64_t capacity, void *stream) {
+                        int64_t capacity, void *stream, bool from_records = false) {
 	FrameDev f;
 	int rc = make_frame(frame, f);
 	if (rc) return rc;
@@ -176,7 +176,10 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
 	if (num_instances) *num_instances = 0;
 	if (!out_color || !out_depth || !out_alpha || (f.S > 0 && !out_semantic)) return fail(SGR_EINVAL, "output image pointer is NULL");
 	if (!f.bg || !f.view || !f.proj || !f.campos) return fail(SGR_EINVAL, "camera pointer (bg/viewmatrix/projmatrix/campos) is NULL");
-	if (f.P > 0) {
+	if (f.P > 0 && from_records) {
+		if (!radii) return fail(SGR_EINVAL, "radii is NULL");
+		if (f.S > 0 && !semantics) return fail(SGR_EINVAL, "S > 0 but semantics is NULL");
+	} else if (f.P > 0) {
 		if (!means3D || !opacities || !radii) return fail(SGR_EINVAL, "means3D / opacities / radii is NULL");
 		if ((shs == nullptr) == (colors_precomp == nullptr)) return fail(SGR_EINVAL, "provide exactly one of shs / colors_precomp");
 		const bool sr = scales != nullptr && rotations != nullptr;
@@ -199,8 +202,10 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
 	int64_t R = 0;
 	BinView b = carve_bin(nullptr, 0);
 	if (f.P > 0) {
-		SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
-		        "preprocess_fwd");
+		if (from_records) SGR_TRY(launch_count_tiles(f, g, radii, st), "count_tiles");
+		else
+			SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
+			        "preprocess_fwd");
 		SGR_TRY(launch_depth_order(f, g, st), "depth_order");
 		if (!bounded) {
 			uint32_t r32 = 0;
@@ -246,6 +251,39 @@ int sgr_forward_bounded(const SgrFrame *frame, const float *means3D, const float
 	return forward_impl(frame, means3D, shs, colors_precomp, semantics, opacities, scales, rotations, cov3D_precomp, out_color, out_depth,
 	                    out_alpha, out_semantic, radii, geom_state, geom_bytes, img_state, img_bytes, nullptr, nullptr, nullptr, nullptr,
 	                    binning_state, binning_bytes, capacity, stream);
+}
+
+size_t sgr_record_bytes(void) { return sizeof(GaussRec); }
+
+int sgr_project(const SgrFrame *frame, const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
+                const float *scales, const float *rotations, const float *cov3D_precomp, int32_t *radii, void *records, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (f.P == 0) return SGR_OK;
+	if (!f.view || !f.proj || !f.campos) return fail(SGR_EINVAL, "camera pointer (viewmatrix/projmatrix/campos) is NULL");
+	if (!means3D || !opacities || !radii || !records) return fail(SGR_EINVAL, "means3D / opacities / radii / records is NULL");
+	if ((shs == nullptr) == (colors_precomp == nullptr)) return fail(SGR_EINVAL, "provide exactly one of shs / colors_precomp");
+	const bool sr = scales != nullptr && rotations != nullptr;
+	if (sr == (cov3D_precomp != nullptr) || ((scales != nullptr) != (rotations != nullptr)))
+		return fail(SGR_EINVAL, "provide exactly one of (scales, rotations) / cov3D_precomp");
+	if (shs && f.M <= 0) return fail(SGR_EINVAL, "shs given but M == 0");
+	SGR_TRY(launch_project(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii,
+	                       reinterpret_cast<GaussRec *>(records), st),
+	        "project");
+	return SGR_OK;
+}
+
+int sgr_forward_records(const SgrFrame *frame, const int32_t *radii, const float *semantics, float *out_color, float *out_depth,
+                        float *out_alpha, float *out_semantic, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes,
+                        sgr_alloc_fn alloc, void *alloc_user, void **binning_state_out, int64_t *num_instances, void *binning_state,
+                        size_t binning_bytes, int64_t capacity, void *stream) {
+	return forward_impl(frame, nullptr, nullptr, nullptr, semantics, nullptr, nullptr, nullptr, nullptr, out_color, out_depth, out_alpha,
+	                    out_semantic, const_cast<int32_t *>(radii), geom_state, geom_bytes, img_state, img_bytes, alloc, alloc_user,
+	                    binning_state_out, num_instances, capacity >= 0 ? binning_state : nullptr, capacity >= 0 ? binning_bytes : 0,
+	                    capacity >= 0 ? capacity : -1, stream, true);
 }
 
 int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream) {

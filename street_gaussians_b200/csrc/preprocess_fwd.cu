@@ -156,6 +156,8 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float
 	return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
 }
 
+// COUNT = false: records + radii only (sgr_project; the tile counts are taken after the all-gather, per band)
+template <bool COUNT>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, const float *__restrict__ means3D,
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,
                                                              const float *__restrict__ opacities, const float *__restrict__ scales,
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		}
 		radii[idx] = pr.radius;
 	}
+	if (!COUNT) return;
 	uint32_t count = 0;
 	visit_tiles<false, uint32_t>(pr.ok, pr.x0, pr.y0, pr.x1, pr.y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
 	if (in_range) {
@@ -231,8 +234,16 @@ cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const
                                   const float *opacities, const float *scales, const float *rotations,
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
-	preprocess_fwd_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
-	                                                            cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
+	preprocess_fwd_kernel<true><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
+	                                                                  cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
+	return cudaGetLastError();
+}
+cudaError_t launch_project(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
+                           const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp,
+                           int32_t *radii, GaussRec *rec, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	preprocess_fwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
+	                                                                   cov3D_precomp, radii, rec, nullptr, nullptr, nullptr);
 	return cudaGetLastError();
 }
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,

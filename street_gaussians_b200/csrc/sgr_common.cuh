@@ -144,10 +144,16 @@ struct FrameDev {  // SgrFrame + derived values, passed by value to kernels
 cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
                                   const float *opacities, const float *scales, const float *rotations,
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st);
+// records + radii only (no tile counts): step 1 of the Gaussian-sharded forward
+cudaError_t launch_project(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
+                           const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp,
+                           int32_t *radii, GaussRec *rec, cudaStream_t st);
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
 cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
+// Gaussian-sharded mode: tile counts / depth keys of gathered records against this rank's band (binning.cu)
+cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st);
 size_t geom_temp_bytes(int P);
 size_t sort_temp_bytes(int64_t R);
 // cap < 0: exact mode, R is the host-known instance count.  cap >= 0: bounded mode, R is ignored, the arrays hold `cap`

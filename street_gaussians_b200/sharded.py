@@ -9,15 +9,30 @@ single-GPU).  One process per GPU (torch.distributed); Gaussian parameters are r
             ("Variant B" of SURVEY.md §8e: 48 B/Gaussian on the wire instead of a 248 B/Gaussian all-gather).
 
 Rows are dealt cyclically (row r -> rank r % world) so a horizon-heavy street scene balances without a histogram.
+
+GaussianShardedRasterizer ("variant A" of SURVEY.md §8e) additionally partitions the GAUSSIANS: every rank owns P/N of them
+(parameters, optimiser state and gradients stay sharded, as in a ZeRO-style trainer) and a tile-row band.
+
+  forward : project own Gaussians -> 48-B screen-space records; all-gather records + radii (NCCL); count / sort / blend
+            the own band from the gathered records.
+  backward: blend_bwd over the own band -> partial grad2d[P_total,12]; ONE reduce-scatter hands every rank the summed
+            rows of its own Gaussians; the per-Gaussian chain rule then runs on P/N Gaussians only.
+
+Compared with ShardedGaussianRasterizer no per-Gaussian stage is replicated any more (preprocess fwd/bwd were 0.42 ms of a
+1.3 ms step at N = 8) and the 2x91 MB all-reduce becomes a 91 MB all-gather plus a 91 MB reduce-scatter.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import torch
 import torch.distributed as dist
+import torch.nn as nn
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, TileRowBand
+from . import _capi
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, InstanceCapacity, TileRowBand, _ForwardState,
+                         _backward_blend_impl, _backward_geom_impl, _dev_f32, _make_frame, _none_if_empty, _ptr, _stream)
 
 
 def cyclic_band(image_height: int, rank: int, world: int) -> TileRowBand:
@@ -73,3 +88,262 @@ def band_of_rows(image_height: int, rank: int, world: int, layout: str = "cyclic
     rows = torch.arange((int(image_height) + 15) // 16)
     own = (rows >= band.begin) & (rows < band.end) & (((rows - band.begin) % max(band.step, 1)) == 0)
     return own.repeat_interleave(16)[: int(image_height)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Gaussian-sharded mode: low-level steps (each is one C-ABI call; tests drive them directly to emulate N ranks on one GPU)
+# ---------------------------------------------------------------------------------------------------------------------
+REC_FLOATS = 12  # sgr_record_bytes() / 4
+
+
+def chunk_size(P_local: int, group=None) -> int:
+    """COLLECTIVE: the common slot count per rank (max of the local Gaussian counts; smaller ranks pad with radii == 0)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(P_local)
+    t = torch.tensor([int(P_local)], dtype=torch.int64, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def _local_tensors(means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp):
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise _capi.SgrError("street_gaussians_b200 rasterizer needs CUDA tensors (there is no CPU fallback)")
+    device = means3D.device
+    S = int(semantics.shape[1]) if (semantics is not None and semantics.dim() == 2) else 0
+    tensors = dict(means3D=_dev_f32(means3D, device), opacities=_dev_f32(opacities, device))
+    for name, t in (("sh", _none_if_empty(sh)), ("colors_precomp", _none_if_empty(colors_precomp)), ("scales", _none_if_empty(scales)),
+                    ("rotations", _none_if_empty(rotations)), ("cov3Ds_precomp", _none_if_empty(cov3Ds_precomp)),
+                    ("semantics", semantics if S > 0 else None)):
+        tensors[name] = _dev_f32(t, device) if t is not None else None
+    return tensors
+
+
+def project_records(tensors, settings: GaussianRasterizationSettings, chunk: int):
+    """Step 1 (sgr_project): records[chunk,12] float32 view + radii[chunk] int32 of the local Gaussians; slots past
+    P_local are padding (radii == 0)."""
+    L = _capi.lib()
+    means3D = tensors["means3D"]
+    device, P = means3D.device, int(means3D.shape[0])
+    if P > chunk:
+        raise _capi.SgrError(f"{P} local Gaussians do not fit the per-rank chunk of {chunk}; call repartition()")
+    rec = torch.empty((chunk, REC_FLOATS), device=device, dtype=torch.float32)
+    radii = (torch.empty if P == chunk else torch.zeros)((chunk,), device=device, dtype=torch.int32)
+    M = int(tensors["sh"].shape[1]) if tensors["sh"] is not None else 0
+    fr, keep = _make_frame(settings, P, M, 0, device, None)
+    with torch.cuda.device(device):
+        rc = L.sgr_project(C.byref(fr), _ptr(means3D), _ptr(tensors["sh"]), _ptr(tensors["colors_precomp"]), _ptr(tensors["opacities"]),
+                           _ptr(tensors["scales"]), _ptr(tensors["rotations"]), _ptr(tensors["cov3Ds_precomp"]), _ptr(radii), _ptr(rec),
+                           _stream(device))
+    _capi.check(rc, "sgr_project")
+    del keep
+    return rec, radii
+
+
+def alloc_gathered(settings: GaussianRasterizationSettings, P_total: int, S: int, device):
+    """Forward state for P_total gathered Gaussians.  Returns (state, records view [P_total,12] float32 into state.geom —
+    the all-gather target —, geom_bytes, img_bytes)."""
+    L = _capi.lib()
+    fr, keep = _make_frame(settings, P_total, 0, S, device, None)
+    gb, ib = C.c_size_t(0), C.c_size_t(0)
+    _capi.check(L.sgr_state_sizes(C.byref(fr), C.byref(gb), C.byref(ib)), "sgr_state_sizes")
+    st = _ForwardState()
+    st.geom = torch.empty((gb.value,), device=device, dtype=torch.uint8)
+    st.img = torch.empty((ib.value,), device=device, dtype=torch.uint8)
+    st.binning, st.num_instances = None, 0
+    rec_all = st.geom[: P_total * REC_FLOATS * 4].view(torch.float32).view(P_total, REC_FLOATS)
+    del keep
+    return st, rec_all, gb.value, ib.value
+
+
+def forward_records(settings: GaussianRasterizationSettings, band: Optional[TileRowBand], st: _ForwardState, sizes, radii_all,
+                    semantics_all, capacity: Optional[InstanceCapacity] = None):
+    """Step 3 (sgr_forward_records): bin / sort / blend `band` from the records already gathered into st.geom."""
+    L = _capi.lib()
+    device, P = radii_all.device, int(radii_all.shape[0])
+    H, W = int(settings.image_height), int(settings.image_width)
+    S = int(semantics_all.shape[1]) if semantics_all is not None else 0
+    f32 = dict(device=device, dtype=torch.float32)
+    alloc_img = torch.empty if band is None else torch.zeros
+    color, depth, alpha, semantic = alloc_img((3, H, W), **f32), alloc_img((1, H, W), **f32), alloc_img((1, H, W), **f32), alloc_img((S, H, W), **f32)
+    fr, keep = _make_frame(settings, P, 0, S, device, band)
+    gb, ib = sizes
+    if capacity is not None:
+        capacity.check()
+    bounded = capacity is not None and capacity.capacity is not None
+    cap = int(capacity.capacity) if bounded else -1
+    nbytes = 0
+    if bounded:
+        nbytes = int(L.sgr_binning_bytes(cap))
+        st.binning = torch.empty((nbytes,), device=device, dtype=torch.uint8)
+
+    def _alloc(_user, n):
+        st.binning = torch.empty((int(n),), device=device, dtype=torch.uint8)
+        return st.binning.data_ptr()
+
+    cb = _capi.ALLOC_FN() if bounded else _capi.ALLOC_FN(_alloc)
+    bin_ptr, n_inst = C.c_void_p(), C.c_int64(0)
+    with torch.cuda.device(device):
+        rc = L.sgr_forward_records(C.byref(fr), _ptr(radii_all), _ptr(semantics_all), _ptr(color), _ptr(depth), _ptr(alpha), _ptr(semantic),
+                                   _ptr(st.geom), gb, _ptr(st.img), ib, cb, None, C.byref(bin_ptr), C.byref(n_inst),
+                                   _ptr(st.binning) if bounded else None, nbytes, cap, _stream(device))
+        _capi.check(rc, "sgr_forward_records")
+        if bounded:
+            host_status = torch.zeros(2, dtype=torch.int32).pin_memory()
+            rc = L.sgr_forward_status_async(C.byref(fr), _ptr(st.geom), C.c_void_p(host_status.data_ptr()), _stream(device))
+            _capi.check(rc, "sgr_forward_status_async")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            capacity.track(host_status, ev)
+            st.num_instances = cap
+        else:
+            st.num_instances = int(n_inst.value)
+            if capacity is not None:
+                capacity.observe(st.num_instances)
+    del keep
+    return color, depth, alpha, semantic
+
+
+def backward_blend_records(settings, band, st: _ForwardState, P_total: int, semantics_all, alpha, grad_color, grad_depth, grad_alpha,
+                           grad_semantic):
+    """Step 4: partial grad2d[P_total,12] (+ dL_dsemantics[P_total,S]) of this rank's band."""
+    shim = dict(means3D=torch.empty((P_total, 0), device=alpha.device), semantics=semantics_all, sh=None)
+    return _backward_blend_impl(settings, band, st, shim, alpha, grad_color, grad_depth, grad_alpha, grad_semantic)
+
+
+def backward_geom_local(settings, tensors, rec_local, radii_local, grad2d_local):
+    """Step 5: chain rule for the local Gaussians from their own records and their reduced grad2d rows."""
+    P = int(tensors["means3D"].shape[0])
+    st = _ForwardState()
+    st.geom = rec_local  # sgr_backward_geom reads only the record array, which sits at offset 0 of a geom_state
+    local = dict(tensors)
+    local["semantics"] = None
+    return _backward_geom_impl(settings, None, st, local, radii_local[:P], grad2d_local[:P].contiguous())
+
+
+class _GaussianShardedRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp, settings, owner):
+        tensors = _local_tensors(means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp)
+        device, P = means3D.device, int(means3D.shape[0])
+        world, chunk, group = owner.world, owner.chunk_for(P), owner.group
+        S = int(tensors["semantics"].shape[1]) if tensors["semantics"] is not None else 0
+        rec, radii = project_records(tensors, settings, chunk)
+        P_total = chunk * world
+        st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
+        radii_all = torch.empty((P_total,), device=device, dtype=torch.int32)
+        sem_all = None
+        if world > 1:
+            dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1), group=group)
+            dist.all_gather_into_tensor(radii_all, radii, group=group)
+        else:
+            rec_all.copy_(rec)
+            radii_all.copy_(radii)
+        if S > 0:
+            sem_local = tensors["semantics"]
+            if P < chunk:
+                sem_local = torch.cat([sem_local, sem_local.new_zeros((chunk - P, S))])
+            sem_all = torch.empty((P_total, S), device=device, dtype=torch.float32)
+            if world > 1:
+                dist.all_gather_into_tensor(sem_all.view(-1), sem_local.contiguous().view(-1), group=group)
+            else:
+                sem_all.copy_(sem_local)
+        color, depth, alpha, semantic = forward_records(settings, owner.band, st, (gb, ib), radii_all, sem_all, owner.capacity)
+        ctx.settings, ctx.owner, ctx.state, ctx.tensors = settings, owner, st, tensors
+        ctx.sem_all, ctx.P_total, ctx.chunk = sem_all, P_total, chunk
+        ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype)
+                           for t in (means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp))
+        ctx.save_for_backward(rec, radii, alpha)
+        radii_out = radii[:P]
+        ctx.mark_non_differentiable(radii_out)
+        return color, radii_out, depth, alpha, semantic
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha, grad_semantic):
+        rec, radii, alpha = ctx.saved_tensors
+        settings, owner, st, tensors, shapes = ctx.settings, ctx.owner, ctx.state, ctx.tensors, ctx.shapes
+        dev = alpha.device
+        H, W = int(settings.image_height), int(settings.image_width)
+        S = int(ctx.sem_all.shape[1]) if ctx.sem_all is not None else 0
+        P = int(tensors["means3D"].shape[0])
+        zimg = lambda c: torch.zeros((c, H, W), device=dev, dtype=torch.float32)
+        grad_color = grad_color if grad_color is not None else zimg(3)
+        grad_depth = grad_depth if grad_depth is not None else zimg(1)
+        grad_alpha = grad_alpha if grad_alpha is not None else zimg(1)
+        grad_semantic = grad_semantic if grad_semantic is not None else zimg(S)
+        grad2d, g_sem = backward_blend_records(settings, owner.band, st, ctx.P_total, ctx.sem_all, alpha, grad_color, grad_depth,
+                                               grad_alpha, grad_semantic)
+        if owner.world > 1:
+            g2_local = torch.empty((ctx.chunk, 12), device=dev, dtype=torch.float32)
+            dist.reduce_scatter_tensor(g2_local.view(-1), grad2d.view(-1), op=dist.ReduceOp.SUM, group=owner.group)
+            if S > 0:
+                gs_local = torch.empty((ctx.chunk, S), device=dev, dtype=torch.float32)
+                dist.reduce_scatter_tensor(gs_local.view(-1), g_sem.view(-1), op=dist.ReduceOp.SUM, group=owner.group)
+                g_sem = gs_local
+            grad2d = g2_local
+        if P == 0:
+            g = (None,) * 8
+        else:
+            g = backward_geom_local(settings, tensors, rec, radii, grad2d)
+        g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov = g
+
+        def fit(t, i):
+            if shapes[i] is None:
+                return None
+            shape, device, dtype = shapes[i]
+            if t is None:
+                return torch.zeros(shape, device=device, dtype=dtype)
+            return t.reshape(shape).to(device=device, dtype=dtype)
+
+        return (fit(g_means3D, 0), fit(g_means2D, 1), fit(g_sh, 2), fit(g_colors, 3), fit(g_sem[:P] if S > 0 else None, 4),
+                fit(g_opac, 5), fit(g_scales, 6), fit(g_rots, 7), fit(g_cov, 8), None, None)
+
+
+class GaussianShardedRasterizer(nn.Module):
+    """Same call signature as GaussianRasterizer.forward, but every argument holds only THIS rank's Gaussians and the
+    returned radii / gradients cover only them; the images cover this rank's tile rows (zeros elsewhere).  The gathered
+    order is rank-major, so with rank r holding rows [r*chunk, (r+1)*chunk) of a global array the images are
+    bit-identical to the single-GPU render of that array."""
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings, group: Optional[dist.ProcessGroup] = None,
+                 layout: str = "cyclic", capacity: Optional[InstanceCapacity] = None, chunk: Optional[int] = None):
+        super().__init__()
+        self.raster_settings, self.group, self.capacity = raster_settings, group, capacity
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        mk = cyclic_band if layout == "cyclic" else contiguous_band
+        self.band = mk(raster_settings.image_height, self.rank, self.world) if self.world > 1 else None
+        self.chunk = int(chunk) if chunk else None
+
+    def repartition(self, P_local: int) -> int:
+        """COLLECTIVE: agree on the per-rank slot count after the local Gaussian count changed (densify / prune)."""
+        self.chunk = chunk_size(P_local, self.group)
+        return self.chunk
+
+    def chunk_for(self, P_local: int) -> int:
+        if self.chunk is None:  # first forward: every rank is here together
+            self.repartition(P_local)
+        return self.chunk
+
+    def synchronize_capacity(self):
+        if self.capacity is not None:
+            self.capacity.check(wait=True)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
+                semantics=None):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        e = torch.Tensor([])
+        shs = e if shs is None else shs
+        colors_precomp = e if colors_precomp is None else colors_precomp
+        scales = e if scales is None else scales
+        rotations = e if rotations is None else rotations
+        cov3D_precomp = e if cov3D_precomp is None else cov3D_precomp
+        if semantics is None:
+            semantics = torch.zeros((means3D.shape[0], 0), device=means3D.device)
+        return _GaussianShardedRasterize.apply(means3D, means2D, shs, colors_precomp, semantics, opacities, scales, rotations,
+                                               cov3D_precomp, self.raster_settings, self)

@@ -257,6 +257,111 @@ def test_sharded_backward_sums_to_whole():
         assert util.rel_err(parts, whole) < 1e-5
 
 
+@pytest.mark.parametrize("S,world,layout", [(0, 3, "cyclic"), (3, 4, "contiguous")])
+def test_gaussian_sharded_emulated_ranks_match_single_gpu(S, world, layout):
+    """Gaussian-sharded mode (sgr_project / sgr_forward_records; SURVEY.md §8e variant A) with the N ranks played one after
+    the other on one GPU: concatenation stands in for the all-gather, a sum + slice for the reduce-scatter.  Forward
+    images must be BIT-identical to the single-GPU render, gradients equal up to float summation order."""
+    from street_gaussians_b200 import rasterizer as R
+    from street_gaussians_b200 import sharded as SH
+    P = 50_001  # not divisible by the world size -> the last rank carries padding slots
+    scene = synthetic.make_scene(P=P, width=800, height=608, sh_degree=3, seed=52, pose=True, semantics=S)
+    dev = "cuda"
+    st = util.settings_from(sgb, scene["cam"], dev)
+    t = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations", "grad_color", "grad_depth", "grad_alpha")}
+    sem = scene["semantics"].to(dev) if S > 0 else None
+    g_sem_img = scene["grad_semantic"].to(dev) if S > 0 else None
+    with torch.no_grad():
+        col, rad, dep, alp, se, fst, tens = R._forward_impl(t["means3D"], t["shs"], None, sem, t["opacities"], t["scales"], t["rotations"],
+                                                           None, st, None)
+        g2d, gsem = R._backward_blend_impl(st, None, fst, tens, alp, t["grad_color"], t["grad_depth"], t["grad_alpha"], g_sem_img)
+        ref_grads = R._backward_geom_impl(st, None, fst, tens, rad, g2d)
+
+        chunk = (P + world - 1) // world
+        P_total = chunk * world
+        local, recs, radii = [], [], []
+        for r in range(world):
+            sl = slice(r * chunk, min(P, (r + 1) * chunk))
+            lt = SH._local_tensors(t["means3D"][sl], t["shs"][sl], None, sem[sl] if S > 0 else None, t["opacities"][sl], t["scales"][sl],
+                                   t["rotations"][sl], None)
+            rec_r, rad_r = SH.project_records(lt, st, chunk)
+            local.append(lt); recs.append(rec_r); radii.append(rad_r)
+        rec_cat, radii_all = torch.cat(recs), torch.cat(radii)
+        assert torch.equal(radii_all[:P], rad) and int(radii_all[P:].abs().sum()) == 0
+        sem_all = torch.cat([sem, sem.new_zeros((P_total - P, S))]) if S > 0 else None
+        mk = SH.cyclic_band if layout == "cyclic" else SH.contiguous_band
+        imgs, g2d_sum, gsem_sum = None, 0, 0
+        for r in range(world):
+            band = mk(608, r, world)
+            fs, rec_all, gb, ib = SH.alloc_gathered(st, P_total, S, torch.device(dev))
+            rec_all.copy_(rec_cat)
+            out = SH.forward_records(st, band, fs, (gb, ib), radii_all, sem_all)
+            imgs = out if imgs is None else tuple(a + b for a, b in zip(imgs, out))
+            part, part_sem = SH.backward_blend_records(st, band, fs, P_total, sem_all, out[2], t["grad_color"], t["grad_depth"],
+                                                       t["grad_alpha"], g_sem_img)
+            g2d_sum = g2d_sum + part.double()
+            gsem_sum = gsem_sum + part_sem.double()
+        for a, b, name in zip(imgs, (col, dep, alp, se), ("color", "depth", "alpha", "semantic")):
+            assert torch.equal(a, b), f"{name} differs from the single-GPU render"
+        assert util.rel_err(g2d_sum[:P].cpu().numpy(), g2d.double().cpu().numpy()) < 1e-5
+        assert float(g2d_sum[P:].abs().max()) == 0.0 if P_total > P else True
+        if S > 0:
+            assert util.rel_err(gsem_sum[:P].cpu().numpy(), gsem.double().cpu().numpy()) < 1e-5
+        parts = []
+        for r in range(world):
+            g_slice = g2d_sum[r * chunk:(r + 1) * chunk].float().contiguous()
+            parts.append(SH.backward_geom_local(st, local[r], recs[r], radii[r], g_slice))
+        for i, ref in enumerate(ref_grads):
+            if ref is None:
+                assert all(p[i] is None for p in parts)
+                continue
+            got = torch.cat([p[i] for p in parts])
+            assert got.shape == ref.shape
+            assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, i
+
+
+def test_gaussian_sharded_module_world1_matches_plain_rasterizer():
+    """GaussianShardedRasterizer without a process group (world 1) runs the project -> records -> local chain-rule path end
+    to end through autograd and must reproduce GaussianRasterizer."""
+    from street_gaussians_b200.sharded import GaussianShardedRasterizer
+    scene = synthetic.make_scene(P=20_000, width=640, height=400, sh_degree=2, seed=53, pose=True, semantics=2)
+    dev = "cuda"
+    st = util.settings_from(sgb, scene["cam"], dev)
+    res = {}
+    for name, mod in (("plain", sgb.GaussianRasterizer(st)), ("sharded", GaussianShardedRasterizer(st)),
+                      ("sharded_bounded", GaussianShardedRasterizer(st, capacity=sgb.InstanceCapacity()))):
+        for rep in range(2 if name == "sharded_bounded" else 1):  # second call of the bounded module runs sync-free
+            leaves = {k: scene[k].to(dev).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations", "semantics")}
+            m2d = torch.zeros(20_000, 3, device=dev, requires_grad=True)
+            color, radii, depth, alpha, semantic = mod(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                                        shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                                                        semantics=leaves["semantics"])
+            loss = (color * scene["grad_color"].to(dev)).sum() + (depth * scene["grad_depth"].to(dev)).sum() + \
+                (alpha * scene["grad_alpha"].to(dev)).sum() + (semantic * scene["grad_semantic"].to(dev)).sum()
+            loss.backward()
+        mod.synchronize_capacity() if hasattr(mod, "synchronize_capacity") else None
+        res[name] = dict(color=color.detach(), radii=radii, depth=depth.detach(), alpha=alpha.detach(), semantic=semantic.detach(),
+                         grads={k: v.grad for k, v in leaves.items()}, m2d=m2d.grad)
+    for name in ("sharded", "sharded_bounded"):
+        for k in ("color", "radii", "depth", "alpha", "semantic"):
+            assert torch.equal(res[name][k], res["plain"][k]), (name, k)
+        for k, g in res["plain"]["grads"].items():
+            assert util.rel_err(res[name]["grads"][k].double().cpu().numpy(), g.double().cpu().numpy()) < 2e-5, (name, k)
+        assert util.rel_err(res[name]["m2d"].double().cpu().numpy(), res["plain"]["m2d"].double().cpu().numpy()) < 2e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL all-gather / reduce-scatter)")
+def test_gaussian_sharded_two_ranks_nccl():
+    """tools/check_gaussian_sharded.py under torchrun on 2 GPUs: GaussianShardedRasterizer vs the single-GPU rasterizer."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "check_gaussian_sharded.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "GAUSSIAN_SHARDED_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_edge_cases():
     dev = "cuda"
     cam = synthetic.make_camera(100, 60, sh_degree=1, bg=(0.1, 0.2, 0.3))

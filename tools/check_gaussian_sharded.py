@@ -1,0 +1,106 @@
+"""torchrun check of the Gaussian-sharded multi-GPU mode against the single-GPU rasterizer on the same seeded scene.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/check_gaussian_sharded.py
+
+Every rank renders the WHOLE scene with GaussianRasterizer (the checker) and its own share with
+GaussianShardedRasterizer (NCCL all-gather of records / reduce-scatter of grad2d).  Own image rows must be bit-identical,
+foreign rows zero, and the gradients of the rank's own Gaussians equal up to float summation order.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import street_gaussians_b200 as sgb  # noqa: E402
+from street_gaussians_b200 import synthetic  # noqa: E402
+from street_gaussians_b200.sharded import GaussianShardedRasterizer, band_of_rows  # noqa: E402
+import util  # noqa: E402
+
+KEYS = ("means3D", "shs", "opacities", "scales", "rotations")
+
+
+def run_case(rank, world, dev, S, P, W, H, bounded):
+    scene = synthetic.make_scene(P=P, width=W, height=H, sh_degree=3, seed=77, pose=True, semantics=S)
+    st = util.settings_from(sgb, scene["cam"], dev)
+    chunk = (P + world - 1) // world
+    lo, hi = min(P, rank * chunk), min(P, (rank + 1) * chunk)
+    rows = band_of_rows(H, rank, world).to(dev)
+    m = rows.view(1, H, 1).float()
+    up = {k: scene[k].to(dev) for k in ("grad_color", "grad_depth", "grad_alpha")}
+    up_sem = scene["grad_semantic"].to(dev) if S else None
+
+    # checker: whole scene on this GPU, upstream gradients of ALL bands (the job-wide loss)
+    full = {k: scene[k].to(dev).requires_grad_(True) for k in KEYS}
+    sem_full = scene["semantics"].to(dev).requires_grad_(True) if S else None
+    m2d_full = torch.zeros(P, 3, device=dev, requires_grad=True)
+    ref = sgb.GaussianRasterizer(st)(means3D=full["means3D"], means2D=m2d_full, opacities=full["opacities"], shs=full["shs"],
+                                     scales=full["scales"], rotations=full["rotations"], semantics=sem_full)
+    outs, grads = [ref[0], ref[2], ref[3]], [up["grad_color"], up["grad_depth"], up["grad_alpha"]]
+    if S:
+        outs.append(ref[4]); grads.append(up_sem)
+    torch.autograd.backward(outs, grads)
+
+    cap = sgb.InstanceCapacity() if bounded else None
+    rast = GaussianShardedRasterizer(st, capacity=cap)
+    worst = 0.0
+    for rep in range(2 if bounded else 1):  # second pass of the bounded variant runs without any host sync
+        loc = {k: scene[k][lo:hi].to(dev).requires_grad_(True) for k in KEYS}
+        sem_loc = scene["semantics"][lo:hi].to(dev).requires_grad_(True) if S else None
+        m2d = torch.zeros(hi - lo, 3, device=dev, requires_grad=True)
+        got = rast(means3D=loc["means3D"], means2D=m2d, opacities=loc["opacities"], shs=loc["shs"], scales=loc["scales"],
+                   rotations=loc["rotations"], semantics=sem_loc)
+        outs, grads = [got[0], got[2], got[3]], [up["grad_color"] * m, up["grad_depth"] * m, up["grad_alpha"] * m]
+        if S:
+            outs.append(got[4]); grads.append(up_sem * m)
+        torch.autograd.backward(outs, grads)
+        rast.synchronize_capacity()
+        assert torch.equal(got[1], ref[1][lo:hi]), "radii"
+        for a, b, name in ((got[0], ref[0], "color"), (got[2], ref[2], "depth"), (got[3], ref[3], "alpha"), (got[4], ref[4], "semantic")):
+            if a.numel() == 0:
+                continue
+            assert torch.equal(a[:, rows], b.detach()[:, rows]), f"{name}: own rows differ"
+            assert float(a[:, ~rows].abs().max()) == 0.0 if (~rows).any() else True, f"{name}: foreign rows not zero"
+        for k in KEYS:
+            e = util.rel_err(loc[k].grad.double().cpu().numpy(), full[k].grad[lo:hi].double().cpu().numpy())
+            worst = max(worst, e)
+            assert e < 3e-5, (k, e)
+        e = util.rel_err(m2d.grad.double().cpu().numpy(), m2d_full.grad[lo:hi].double().cpu().numpy())
+        assert e < 3e-5, ("means2D", e)
+        if S:
+            e = util.rel_err(sem_loc.grad.double().cpu().numpy(), sem_full.grad[lo:hi].double().cpu().numpy())
+            assert e < 3e-5, ("semantics", e)
+    return worst
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    try:
+        for S, P, W, H, bounded in ((0, 200_003, 1280, 720, False), (2, 60_001, 800, 608, False), (0, 200_003, 1280, 720, True)):
+            worst = run_case(rank, world, dev, S, P, W, H, bounded)
+            print(f"[rank {rank}/{world}] S={S} P={P} {W}x{H} bounded={bounded}: images bit-equal, worst grad rel err {worst:.2e}", flush=True)
+    except AssertionError as e:
+        ok = False
+        print(f"[rank {rank}] FAILED: {e!r}", flush=True)
+    if world > 1:
+        flag = torch.tensor([0 if ok else 1], device=dev)
+        dist.all_reduce(flag)
+        ok = int(flag.item()) == 0
+        dist.destroy_process_group()
+    if rank == 0:
+        print("GAUSSIAN_SHARDED_CHECK", "OK" if ok else "FAILED", flush=True)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
