@@ -53,10 +53,11 @@ def parse():
                          "this is the default for the timed region; the exact drop-in mode is timed beside it "
                          "(config.exact_mode_ms_per_step)")
     ap.add_argument("--exact", dest="sync_free", action="store_false", help="force the exact (read-back) mode")
-    ap.add_argument("--mp-mode", choices=["gaussian", "replicated"], default="gaussian",
-                    help="N > 1 only. gaussian: every rank owns P/N Gaussians and a tile-row band (all-gather of records, "
-                         "reduce-scatter of grad2d; GaussianShardedRasterizer).  replicated: parameters replicated, tile rows "
-                         "sharded, one all-reduce (ShardedGaussianRasterizer)")
+    ap.add_argument("--mp-mode", choices=["gaussian", "gaussian-p2p", "replicated"], default="gaussian",
+                    help="N > 1 only. gaussian: every rank owns P/N Gaussians and a tile-row band (NCCL all-gather of records, "
+                         "reduce-scatter of grad2d; GaussianShardedRasterizer).  gaussian-p2p: same partition, but records / grad2d rows "
+                         "move by direct NVLink stores / loads to exactly the ranks that need them (exchange='p2p').  replicated: "
+                         "parameters replicated, tile rows sharded, one all-reduce (ShardedGaussianRasterizer)")
     ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--diag", action="store_true", help="per-rank host/all-reduce timing breakdown on stderr")
     ap.add_argument("--cpu-sample-stride", type=int, default=0, help="CPU baseline uses every k-th Gaussian (0 = auto)")
@@ -230,14 +231,16 @@ def main():
             # what the UNCHANGED reference call site gets — is timed right after and reported as exact_mode_ms_per_step.
             args.sync_free = True
         capacity = mod.InstanceCapacity() if args.sync_free else None
-        if use_dist and args.mp_mode == "gaussian":
+        if use_dist and args.mp_mode.startswith("gaussian"):
             from street_gaussians_b200.sharded import GaussianShardedRasterizer
             chunk = (P + world - 1) // world
-            rast = GaussianShardedRasterizer(make_settings(mod, cam, dev), capacity=capacity, chunk=chunk)
+            rast = GaussianShardedRasterizer(make_settings(mod, cam, dev), capacity=capacity, chunk=chunk,
+                                             exchange="p2p" if args.mp_mode == "gaussian-p2p" else "nccl")
         else:
             rast = ShardedGaussianRasterizer(make_settings(mod, cam, dev), capacity=capacity)
 
-    gauss_sharded = use_dist and args.mp_mode == "gaussian" and not ref_cuda
+    gauss_sharded = use_dist and args.mp_mode.startswith("gaussian") and not ref_cuda
+    p2p = gauss_sharded and args.mp_mode == "gaussian-p2p"
     lo, hi = (min(P, rank * chunk), min(P, (rank + 1) * chunk)) if gauss_sharded else (0, P)
     local_scene = {k: scene[k][lo:hi].contiguous() for k in PARAM_KEYS}  # this rank's Gaussians (all of them unless Gaussian-sharded)
     params = {k: local_scene[k].to(dev).requires_grad_(True) for k in PARAM_KEYS}
@@ -336,24 +339,36 @@ def main():
         band = rast.band
         with torch.no_grad():
             lt = SH._local_tensors(params["means3D"], params["shs"], None, None, params["opacities"], params["scales"], params["rotations"], None)
-            names = ("project", "all_gather", "forward_records", "blend_bwd", "reduce_scatter", "preprocess_bwd")
+            names = ("project", "scatter+barrier" if p2p else "all_gather", "forward_records", "blend_bwd",
+                     "barrier+gather" if p2p else "reduce_scatter", "preprocess_bwd")
             acc = {k: [] for k in names}
+            ws = rast.workspace(dev) if p2p else None
             for it in range(3 + 5):
                 evs = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
                 evs[0].record()
                 rec, radii_l = SH.project_records(lt, st_obj, chunk)
                 evs[1].record()
-                fs, rec_all, gb, ib = SH.alloc_gathered(st_obj, chunk * world, 0, dev)
-                radii_all = torch.empty((chunk * world,), device=dev, dtype=torch.int32)
-                dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1))
-                dist.all_gather_into_tensor(radii_all, radii_l)
+                if p2p:
+                    SH.scatter_records(st_obj, ws, rec, radii_l, hi - lo)
+                    ws.barrier()
+                    fs, radii_all, gb, ib = SH.peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
+                else:
+                    fs, rec_all, gb, ib = SH.alloc_gathered(st_obj, chunk * world, 0, dev)
+                    radii_all = torch.empty((chunk * world,), device=dev, dtype=torch.int32)
+                    dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1))
+                    dist.all_gather_into_tensor(radii_all, radii_l)
                 evs[2].record()
                 col, dep, alp, sem = SH.forward_records(st_obj, band, fs, (gb, ib), radii_all, None)
                 evs[3].record()
-                g2d, gsem = SH.backward_blend_records(st_obj, band, fs, chunk * world, None, alp, gc, gd, ga, None)
+                g2d, gsem = SH.backward_blend_records(st_obj, band, fs, chunk * world, None, alp, gc, gd, ga, None,
+                                                      grad2d_out=ws.grad2d if p2p else None)
                 evs[4].record()
-                g2l = torch.empty((chunk, 12), device=dev)
-                dist.reduce_scatter_tensor(g2l.view(-1), g2d.view(-1))
+                if p2p:
+                    ws.barrier()
+                    g2l = SH.gather_grad2d(st_obj, ws, rec, radii_l, hi - lo)
+                else:
+                    g2l = torch.empty((chunk, 12), device=dev)
+                    dist.reduce_scatter_tensor(g2l.view(-1), g2d.view(-1))
                 evs[5].record()
                 SH.backward_geom_local(st_obj, lt, rec, radii_l, g2l)
                 evs[6].record()
@@ -477,8 +492,10 @@ def main():
                     dtype="f32", data="synthetic (seeded; street_gaussians_b200/synthetic.py)",
                     config=dict(workload=wl_desc, P=P, visible=visible, width=W, height=H, sh_degree=cam["sh_degree"],
                                 l2="inputs (%.0f MB of Gaussian parameters) exceed the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6),
-                                parallelism=(("Gaussian-sharded x%d (P/N Gaussians + cyclic tile rows per rank): NCCL all-gather of 48-B records, "
-                                              "reduce-scatter of grad2d[P,12]; parameters and gradients stay sharded" % world) if gauss_sharded else
+                                parallelism=(("Gaussian-sharded x%d (P/N Gaussians + cyclic tile rows per rank): %s; parameters and gradients stay sharded"
+                                              % (world, "48-B records stored / grad2d rows loaded over NVLink peer memory to/from only the ranks whose band "
+                                                        "a Gaussian touches, 2 device-side barriers per step, no NCCL on the data path" if p2p else
+                                                 "NCCL all-gather of 48-B records, reduce-scatter of grad2d[P,12]")) if gauss_sharded else
                                              ("tile-row sharded x%d (cyclic rows), parameters replicated, 1 NCCL all-reduce of grad2d[P,12]/step" % world))
                                 if use_dist else "single GPU",
                                 num_instances=n_inst, gaussians_pixels_per_s=P * W * H * fps, stage_ms=stages,
@@ -486,7 +503,7 @@ def main():
                                 exact_mode_ms_per_step=exact_ms),
                     e2e=dict(value=1000.0 / e2e_ms, unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                              note="pinned host -> device copy of all 59 floats/Gaussian every step (each rank uploads the Gaussians it owns), double-buffered on a copy stream; scalar loss read back"),
-                    gpu_launches=(((21 if args.sync_free else 20) + (1 if gauss_sharded else 0)) * args.steps) if not ref_cuda else 0,
+                    gpu_launches=(((21 if args.sync_free else 20) + (1 if gauss_sharded else 0) + (2 if p2p else 0)) * args.steps) if not ref_cuda else 0,
                     clocks=clocks)
         if roofline:
             line["roofline"] = roofline

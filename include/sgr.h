@@ -178,6 +178,30 @@ int sgr_forward_records(const SgrFrame *frame, const int32_t *radii, const float
                         void *img_state, size_t img_bytes, sgr_alloc_fn alloc, void *alloc_user, void **binning_state_out,
                         int64_t *num_instances, void *binning_state, size_t binning_bytes, int64_t capacity, void *stream);
 
+/* ---- Gaussian-sharded exchange over NVLink peer memory (replaces the two NCCL collectives of steps 2 and 4 above) -----
+ * Requires every rank's gathered arrays to be mapped into every process (CUDA IPC / VMM; the Python host uses
+ * torch.distributed._symmetric_memory) and the CYCLIC band layout: tile row r belongs to rank r % world.
+ *   sgr_scatter_records : for every local slot i (global id g = rank*chunk + i) store the 48-B record into
+ *                         peers.records[p][g] of each rank p whose band meets the Gaussian's tile rectangle, and
+ *                         peers.radii[p][g] = radius for those ranks, 0 for all others (padding slots: 0 everywhere).
+ *   sgr_gather_grad2d   : grad2d_local[i,0:12] = sum over the same ranks p of peers.grad2d[p][g,0:12]; rows of
+ *                         invisible Gaussians are zero.
+ * The caller must order them against the peers' kernels with a cross-rank barrier on the stream: one after
+ * sgr_scatter_records (before any rank's sgr_forward_records) and one after sgr_backward_blend (before any rank's
+ * sgr_gather_grad2d).  Traffic per Gaussian is 48 B x (#ranks it touches) + 4 B x world instead of 48 B x world. */
+#define SGR_MAX_PEERS 16
+typedef struct SgrPeers {
+	int32_t world, rank;
+	int64_t chunk;                      /* slots per rank */
+	void *records[SGR_MAX_PEERS];       /* rank p's gathered record array (= start of its geom_state), world*chunk records */
+	int32_t *radii[SGR_MAX_PEERS];      /* rank p's radii[world*chunk] */
+	const float *grad2d[SGR_MAX_PEERS]; /* rank p's partial grad2d[world*chunk,12] (output of its sgr_backward_blend) */
+} SgrPeers;
+int sgr_scatter_records(const SgrFrame *frame, const SgrPeers *peers, const void *records_local, const int32_t *radii_local,
+                        void *stream);
+int sgr_gather_grad2d(const SgrFrame *frame, const SgrPeers *peers, const void *records_local, const int32_t *radii_local,
+                      float *grad2d_local, void *stream);
+
 /* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
  * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */
 int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,

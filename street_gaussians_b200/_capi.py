@@ -13,7 +13,8 @@ ABI_VERSION = 3
 SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_state_sizes", "sgr_binning_bytes", "sgr_forward", "sgr_forward_bounded",
            "sgr_forward_status", "sgr_forward_status_async", "sgr_backward_blend",
            "sgr_backward_geom", "sgr_backward", "sgr_mark_visible", "sgr_visible_filter", "sgr_knn_scratch_bytes",
-           "sgr_knn_mean_dist2", "sgr_record_bytes", "sgr_project", "sgr_forward_records"]
+           "sgr_knn_mean_dist2", "sgr_record_bytes", "sgr_project", "sgr_forward_records",
+           "sgr_scatter_records", "sgr_gather_grad2d"]
 
 
 class SgrFrame(C.Structure):
@@ -21,6 +22,14 @@ class SgrFrame(C.Structure):
                 ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float), ("prefiltered", C.c_int32),
                 ("debug", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_step", C.c_int32),
                 ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p)]
+
+
+MAX_PEERS = 16
+
+
+class SgrPeers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("chunk", C.c_int64), ("records", C.c_void_p * MAX_PEERS),
+                ("radii", C.c_void_p * MAX_PEERS), ("grad2d", C.c_void_p * MAX_PEERS)]
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -70,6 +79,10 @@ def lib():
     L.sgr_forward_records.argtypes = [C.POINTER(SgrFrame), vp, vp] + [vp] * 4 + [vp, C.c_size_t, vp, C.c_size_t, ALLOC_FN, vp,
                                                                                   C.POINTER(vp), C.POINTER(C.c_int64), vp, C.c_size_t,
                                                                                   C.c_int64, vp]
+    L.sgr_scatter_records.restype = C.c_int
+    L.sgr_scatter_records.argtypes = [C.POINTER(SgrFrame), C.POINTER(SgrPeers), vp, vp, vp]
+    L.sgr_gather_grad2d.restype = C.c_int
+    L.sgr_gather_grad2d.argtypes = [C.POINTER(SgrFrame), C.POINTER(SgrPeers), vp, vp, vp, vp]
     L.sgr_backward_blend.restype = C.c_int
     L.sgr_backward_blend.argtypes = [C.POINTER(SgrFrame), C.c_int64] + [vp] * 12
     L.sgr_backward_geom.restype = C.c_int

@@ -286,6 +286,50 @@ int sgr_forward_records(const SgrFrame *frame, const int32_t *radii, const float
 	                    capacity >= 0 ? capacity : -1, stream, true);
 }
 
+static int make_peers(const SgrPeers *peers, const FrameDev &f, bool need_grad, PeerTable &pt) {
+	if (!peers) return fail(SGR_EINVAL, "peers is NULL");
+	if (peers->world < 1 || peers->world > SGR_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
+		return fail(SGR_EINVAL, "bad peer table: world=%d rank=%d (at most %d ranks)", peers->world, peers->rank, SGR_MAX_PEERS);
+	if (peers->chunk < f.P) return fail(SGR_EINVAL, "chunk %lld smaller than the local Gaussian count %d", (long long)peers->chunk, f.P);
+	if ((long long)peers->chunk * peers->world > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "world*chunk exceeds 2^31-1");
+	pt.world = peers->world; pt.rank = peers->rank; pt.chunk = peers->chunk;
+	for (int p = 0; p < peers->world; p++) {
+		if (!peers->records[p] || !peers->radii[p] || (need_grad && !peers->grad2d[p])) return fail(SGR_EINVAL, "peer table entry %d is NULL", p);
+		pt.rec[p] = reinterpret_cast<GaussRec *>(peers->records[p]);
+		pt.radii[p] = peers->radii[p];
+		pt.grad2d[p] = peers->grad2d[p];
+	}
+	return SGR_OK;
+}
+
+int sgr_scatter_records(const SgrFrame *frame, const SgrPeers *peers, const void *records_local, const int32_t *radii_local, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	PeerTable pt = {};
+	if ((rc = make_peers(peers, f, false, pt)) != SGR_OK) return rc;
+	if (f.P > 0 && (!records_local || !radii_local)) return fail(SGR_EINVAL, "records_local / radii_local is NULL");
+	SGR_TRY(launch_scatter_records(f, pt, reinterpret_cast<const GaussRec *>(records_local), radii_local, st), "scatter_records");
+	return SGR_OK;
+}
+
+int sgr_gather_grad2d(const SgrFrame *frame, const SgrPeers *peers, const void *records_local, const int32_t *radii_local,
+                      float *grad2d_local, void *stream) {
+	FrameDev f;
+	int rc = make_frame(frame, f);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	PeerTable pt = {};
+	if ((rc = make_peers(peers, f, true, pt)) != SGR_OK) return rc;
+	if (f.P == 0) return SGR_OK;
+	if (!records_local || !radii_local || !grad2d_local) return fail(SGR_EINVAL, "NULL pointer passed to sgr_gather_grad2d");
+	SGR_TRY(launch_gather_grad2d(f, pt, reinterpret_cast<const GaussRec *>(records_local), radii_local, grad2d_local, st), "gather_grad2d");
+	return SGR_OK;
+}
+
 int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream) {
 	FrameDev f;
 	int rc = make_frame(frame, f);

@@ -152,6 +152,18 @@ cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
 cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
+// Gaussian-sharded exchange over peer memory (peer_exchange.cu); device copy of include/sgr.h's SgrPeers
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+	int world, rank;
+	long long chunk;
+	GaussRec *rec[kMaxPeers];
+	int32_t *radii[kMaxPeers];
+	const float *grad2d[kMaxPeers];
+};
+cudaError_t launch_scatter_records(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, cudaStream_t st);
+cudaError_t launch_gather_grad2d(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, float *out,
+                                 cudaStream_t st);
 // Gaussian-sharded mode: tile counts / depth keys of gathered records against this rank's band (binning.cu)
 cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st);
 size_t geom_temp_bytes(int P);

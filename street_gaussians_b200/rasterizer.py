@@ -220,15 +220,17 @@ def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rot
     return color, radii, depth, alpha, semantic, st, tensors
 
 
-def _backward_blend_impl(settings, band, st: _ForwardState, tensors, alpha, grad_color, grad_depth, grad_alpha, grad_semantic):
-    """Stage 1: returns (grad2d[P,12], dL_dsemantics[P,S]) — the per-rank partial sums under tile-row sharding."""
+def _backward_blend_impl(settings, band, st: _ForwardState, tensors, alpha, grad_color, grad_depth, grad_alpha, grad_semantic,
+                         grad2d_out: Optional[torch.Tensor] = None):
+    """Stage 1: returns (grad2d[P,12], dL_dsemantics[P,S]) — the per-rank partial sums under tile-row sharding.
+    grad2d_out: write the sums there instead of a fresh tensor (peer-mapped workspace of the Gaussian-sharded mode)."""
     L = _capi.lib()
     means3D = tensors["means3D"]
     device, P = means3D.device, means3D.shape[0]
     S = int(tensors["semantics"].shape[1]) if tensors["semantics"] is not None else 0
     M = int(tensors["sh"].shape[1]) if tensors["sh"] is not None else 0
     fr, keep = _make_frame(settings, P, M, S, device, band)
-    grad2d = torch.empty((P, 12), device=device, dtype=torch.float32)
+    grad2d = grad2d_out if grad2d_out is not None else torch.empty((P, 12), device=device, dtype=torch.float32)
     g_sem = torch.empty((P, S), device=device, dtype=torch.float32)
     gc, gd, ga = _dev_f32(grad_color, device), _dev_f32(grad_depth, device), _dev_f32(grad_alpha, device)
     gs = _dev_f32(grad_semantic, device) if S > 0 else None

@@ -206,10 +206,10 @@ def forward_records(settings: GaussianRasterizationSettings, band: Optional[Tile
 
 
 def backward_blend_records(settings, band, st: _ForwardState, P_total: int, semantics_all, alpha, grad_color, grad_depth, grad_alpha,
-                           grad_semantic):
+                           grad_semantic, grad2d_out=None):
     """Step 4: partial grad2d[P_total,12] (+ dL_dsemantics[P_total,S]) of this rank's band."""
     shim = dict(means3D=torch.empty((P_total, 0), device=alpha.device), semantics=semantics_all, sh=None)
-    return _backward_blend_impl(settings, band, st, shim, alpha, grad_color, grad_depth, grad_alpha, grad_semantic)
+    return _backward_blend_impl(settings, band, st, shim, alpha, grad_color, grad_depth, grad_alpha, grad_semantic, grad2d_out)
 
 
 def backward_geom_local(settings, tensors, rec_local, radii_local, grad2d_local):
@@ -222,6 +222,99 @@ def backward_geom_local(settings, tensors, rec_local, radii_local, grad2d_local)
     return _backward_geom_impl(settings, None, st, local, radii_local[:P], grad2d_local[:P].contiguous())
 
 
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class PeerWorkspace:
+    """Per-rank buffer [geom_state | radii_all | grad2d] that every rank of the group can address (include/sgr.h, SgrPeers).
+
+    Real multi-GPU: ONE torch symmetric-memory allocation per rank (CUDA VMM mapped into every process; NVLink loads and
+    stores), rendezvous'ed once; `barrier()` is the device-side signal-pad barrier of that allocation (~6 us measured on
+    2 x B200).  `emulate(...)` builds `world` ordinary buffers on ONE device that point at each other, so the exchange
+    kernels can be tested without a second GPU."""
+
+    def __init__(self, settings, chunk: int, world: int, rank: int, device, group=None, _buffers=None):
+        self.chunk, self.world, self.rank, self.P_total = int(chunk), int(world), int(rank), int(chunk) * int(world)
+        if world > _capi.MAX_PEERS:
+            raise _capi.SgrError(f"peer exchange supports at most {_capi.MAX_PEERS} ranks, got {world}")
+        self.geom_bytes, self.img_bytes, self.off_radii, self.off_grad, self.total = self.layout(settings, self.P_total, device)
+        self.hdl = None
+        if _buffers is not None:  # single-process emulation: (my buffer, base pointers of all ranks' buffers)
+            self.buf, ptrs = _buffers
+        else:
+            import torch.distributed._symmetric_memory as symm
+            self.buf = symm.empty(self.total, dtype=torch.uint8, device=device)
+            self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            ptrs = list(self.hdl.buffer_ptrs)
+        self.geom = self.buf[: self.geom_bytes]
+        self.radii_all = self.buf[self.off_radii: self.off_radii + 4 * self.P_total].view(torch.int32)
+        self.grad2d = self.buf[self.off_grad: self.off_grad + 48 * self.P_total].view(torch.float32).view(self.P_total, 12)
+        self.peers = _capi.SgrPeers()
+        self.peers.world, self.peers.rank, self.peers.chunk = self.world, self.rank, self.chunk
+        for p in range(self.world):
+            self.peers.records[p] = ptrs[p]
+            self.peers.radii[p] = ptrs[p] + self.off_radii
+            self.peers.grad2d[p] = ptrs[p] + self.off_grad
+
+    @staticmethod
+    def layout(settings, P_total: int, device):
+        """(geom_bytes, img_bytes, offset of radii_all, offset of grad2d, total bytes) of the per-rank buffer."""
+        L = _capi.lib()
+        fr, keep = _make_frame(settings, P_total, 0, 0, device, None)
+        gb, ib = C.c_size_t(0), C.c_size_t(0)
+        _capi.check(L.sgr_state_sizes(C.byref(fr), C.byref(gb), C.byref(ib)), "sgr_state_sizes")
+        del keep
+        off_radii = _align(gb.value)
+        off_grad = _align(off_radii + 4 * P_total)
+        return gb.value, ib.value, off_radii, off_grad, off_grad + 48 * P_total
+
+    @classmethod
+    def emulate(cls, settings, chunk: int, world: int, device):
+        """`world` workspaces on ONE device whose peer tables point at each other (tests; world == 1 module path)."""
+        total = cls.layout(settings, int(chunk) * int(world), device)[4]
+        bufs = [torch.empty(total, dtype=torch.uint8, device=device) for _ in range(world)]
+        ptrs = [b.data_ptr() for b in bufs]
+        return [cls(settings, chunk, world, r, device, _buffers=(bufs[r], ptrs)) for r in range(world)]
+
+    def barrier(self):
+        if self.hdl is not None:
+            self.hdl.barrier(channel=0)
+
+
+def scatter_records(settings, ws: PeerWorkspace, rec_local, radii_local, P_local: int):
+    """Step 2 over peer memory (sgr_scatter_records).  The caller issues ws.barrier() afterwards."""
+    L = _capi.lib()
+    device = rec_local.device
+    fr, keep = _make_frame(settings, P_local, 0, 0, device, None)
+    with torch.cuda.device(device):
+        rc = L.sgr_scatter_records(C.byref(fr), C.byref(ws.peers), _ptr(rec_local), _ptr(radii_local), _stream(device))
+    _capi.check(rc, "sgr_scatter_records")
+    del keep
+
+
+def gather_grad2d(settings, ws: PeerWorkspace, rec_local, radii_local, P_local: int):
+    """Step 4 over peer memory (sgr_gather_grad2d): summed grad2d rows [chunk,12] of the local Gaussians.  The caller has
+    issued ws.barrier() after every rank's backward_blend_records(grad2d_out=ws.grad2d)."""
+    L = _capi.lib()
+    device = rec_local.device
+    out = torch.empty((ws.chunk, 12), device=device, dtype=torch.float32)
+    fr, keep = _make_frame(settings, P_local, 0, 0, device, None)
+    with torch.cuda.device(device):
+        rc = L.sgr_gather_grad2d(C.byref(fr), C.byref(ws.peers), _ptr(rec_local), _ptr(radii_local), _ptr(out), _stream(device))
+    _capi.check(rc, "sgr_gather_grad2d")
+    del keep
+    return out
+
+
+def peer_forward_state(ws: PeerWorkspace):
+    st = _ForwardState()
+    st.geom = ws.geom
+    st.img = torch.empty((ws.img_bytes,), device=ws.buf.device, dtype=torch.uint8)
+    st.binning, st.num_instances = None, 0
+    return st
+
+
 class _GaussianShardedRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp, settings, owner):
@@ -231,10 +324,18 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         S = int(tensors["semantics"].shape[1]) if tensors["semantics"] is not None else 0
         rec, radii = project_records(tensors, settings, chunk)
         P_total = chunk * world
-        st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
-        radii_all = torch.empty((P_total,), device=device, dtype=torch.int32)
+        ws = owner.workspace(device) if owner.exchange == "p2p" else None
         sem_all = None
-        if world > 1:
+        if ws is not None:  # records go straight into the peers' gathered arrays over NVLink
+            scatter_records(settings, ws, rec, radii, P)
+            ws.barrier()
+            st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
+        else:
+            st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
+            radii_all = torch.empty((P_total,), device=device, dtype=torch.int32)
+        if ws is not None:
+            pass
+        elif world > 1:
             dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1), group=group)
             dist.all_gather_into_tensor(radii_all, radii, group=group)
         else:
@@ -251,7 +352,7 @@ class _GaussianShardedRasterize(torch.autograd.Function):
                 sem_all.copy_(sem_local)
         color, depth, alpha, semantic = forward_records(settings, owner.band, st, (gb, ib), radii_all, sem_all, owner.capacity)
         ctx.settings, ctx.owner, ctx.state, ctx.tensors = settings, owner, st, tensors
-        ctx.sem_all, ctx.P_total, ctx.chunk = sem_all, P_total, chunk
+        ctx.sem_all, ctx.P_total, ctx.chunk, ctx.ws = sem_all, P_total, chunk, ws
         ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype)
                            for t in (means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp))
         ctx.save_for_backward(rec, radii, alpha)
@@ -272,9 +373,17 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         grad_depth = grad_depth if grad_depth is not None else zimg(1)
         grad_alpha = grad_alpha if grad_alpha is not None else zimg(1)
         grad_semantic = grad_semantic if grad_semantic is not None else zimg(S)
+        ws = ctx.ws
         grad2d, g_sem = backward_blend_records(settings, owner.band, st, ctx.P_total, ctx.sem_all, alpha, grad_color, grad_depth,
-                                               grad_alpha, grad_semantic)
-        if owner.world > 1:
+                                               grad_alpha, grad_semantic, grad2d_out=ws.grad2d if ws is not None else None)
+        if ws is not None:  # pull the partial rows of the own Gaussians from the ranks that rendered them
+            ws.barrier()
+            grad2d = gather_grad2d(settings, ws, rec, radii, P)
+            if owner.world > 1 and S > 0:
+                gs_local = torch.empty((ctx.chunk, S), device=dev, dtype=torch.float32)
+                dist.reduce_scatter_tensor(gs_local.view(-1), g_sem.view(-1), op=dist.ReduceOp.SUM, group=owner.group)
+                g_sem = gs_local
+        elif owner.world > 1:
             g2_local = torch.empty((ctx.chunk, 12), device=dev, dtype=torch.float32)
             dist.reduce_scatter_tensor(g2_local.view(-1), grad2d.view(-1), op=dist.ReduceOp.SUM, group=owner.group)
             if S > 0:
@@ -307,8 +416,18 @@ class GaussianShardedRasterizer(nn.Module):
     bit-identical to the single-GPU render of that array."""
 
     def __init__(self, raster_settings: GaussianRasterizationSettings, group: Optional[dist.ProcessGroup] = None,
-                 layout: str = "cyclic", capacity: Optional[InstanceCapacity] = None, chunk: Optional[int] = None):
+                 layout: str = "cyclic", capacity: Optional[InstanceCapacity] = None, chunk: Optional[int] = None,
+                 exchange: str = "nccl"):
+        """exchange = "nccl": all-gather of records / reduce-scatter of grad2d.  exchange = "p2p": each record is stored
+        over NVLink into the gathered arrays of only the ranks whose band it touches and the grad2d rows are read back
+        from them (PeerWorkspace; needs torch symmetric memory and the cyclic layout).  With "p2p" the rasterizer owns ONE
+        workspace: a forward's backward must run before the next forward of the same module."""
         super().__init__()
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        if exchange == "p2p" and layout != "cyclic":
+            raise ValueError("the peer-memory exchange needs the cyclic tile-row layout")
+        self.exchange, self._ws = exchange, None
         self.raster_settings, self.group, self.capacity = raster_settings, group, capacity
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -320,6 +439,15 @@ class GaussianShardedRasterizer(nn.Module):
         """COLLECTIVE: agree on the per-rank slot count after the local Gaussian count changed (densify / prune)."""
         self.chunk = chunk_size(P_local, self.group)
         return self.chunk
+
+    def workspace(self, device) -> "PeerWorkspace":
+        """COLLECTIVE on first use and after repartition(): allocate + rendezvous the peer-mapped buffer."""
+        if self._ws is None or self._ws.chunk != self.chunk:
+            if self.world > 1:
+                self._ws = PeerWorkspace(self.raster_settings, self.chunk, self.world, self.rank, device, self.group)
+            else:
+                self._ws = PeerWorkspace.emulate(self.raster_settings, self.chunk, 1, device)[0]
+        return self._ws
 
     def chunk_for(self, P_local: int) -> int:
         if self.chunk is None:  # first forward: every rank is here together

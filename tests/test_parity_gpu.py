@@ -320,6 +320,65 @@ def test_gaussian_sharded_emulated_ranks_match_single_gpu(S, world, layout):
             assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, i
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_gaussian_sharded_peer_exchange_emulated_ranks(world):
+    """The NVLink peer-memory exchange (sgr_scatter_records / sgr_gather_grad2d) with the N ranks' workspaces living on ONE
+    GPU and pointing at each other: images bit-identical to the single-GPU render, every rank receives exactly the
+    Gaussians whose tile rectangle meets its band, gradients equal up to float summation order."""
+    from street_gaussians_b200 import rasterizer as R
+    from street_gaussians_b200 import sharded as SH
+    P, H, W = 50_001, 608, 800
+    scene = synthetic.make_scene(P=P, width=W, height=H, sh_degree=3, seed=54, pose=True)
+    dev = torch.device("cuda")
+    st = util.settings_from(sgb, scene["cam"], dev)
+    t = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations", "grad_color", "grad_depth", "grad_alpha")}
+    with torch.no_grad():
+        col, rad, dep, alp, se, fst, tens = R._forward_impl(t["means3D"], t["shs"], None, None, t["opacities"], t["scales"], t["rotations"],
+                                                           None, st, None)
+        g2d, _ = R._backward_blend_impl(st, None, fst, tens, alp, t["grad_color"], t["grad_depth"], t["grad_alpha"], None)
+        ref_grads = R._backward_geom_impl(st, None, fst, tens, rad, g2d)
+
+        chunk = (P + world - 1) // world
+        wss = SH.PeerWorkspace.emulate(st, chunk, world, dev)
+        for ws in wss:  # poison: stale records / radii from "earlier frames" must not leak into this one
+            ws.buf.fill_(0x7f)
+        local, recs, radii = [], [], []
+        for r in range(world):
+            sl = slice(r * chunk, min(P, (r + 1) * chunk))
+            lt = SH._local_tensors(t["means3D"][sl], t["shs"][sl], None, None, t["opacities"][sl], t["scales"][sl], t["rotations"][sl], None)
+            rec_r, rad_r = SH.project_records(lt, st, chunk)
+            SH.scatter_records(st, wss[r], rec_r, rad_r, int(lt["means3D"].shape[0]))
+            local.append(lt); recs.append(rec_r); radii.append(rad_r)
+        delivered = torch.zeros(P, dtype=torch.int32, device=dev)
+        imgs = None
+        for r in range(world):
+            ws = wss[r]
+            got = ws.radii_all[:P]
+            assert bool(((got == 0) | (got == rad)).all()) and int(ws.radii_all[P:].abs().sum()) == 0
+            delivered += (got > 0).int()
+            fs = SH.peer_forward_state(ws)
+            out = SH.forward_records(st, SH.cyclic_band(H, r, world), fs, (ws.geom_bytes, ws.img_bytes), ws.radii_all, None)
+            imgs = out if imgs is None else tuple(a + b for a, b in zip(imgs, out))
+            SH.backward_blend_records(st, SH.cyclic_band(H, r, world), fs, chunk * world, None, out[2], t["grad_color"], t["grad_depth"],
+                                      t["grad_alpha"], None, grad2d_out=ws.grad2d)
+        assert bool(((delivered > 0) == (rad > 0)).all())  # every visible Gaussian reached at least one rank, no invisible one did
+        assert float(delivered.float().mean()) < 0.75 * world * float((rad > 0).float().mean()) or world == 2  # sparse, not an all-gather
+        for a, b, name in zip(imgs, (col, dep, alp), ("color", "depth", "alpha")):
+            assert torch.equal(a, b), f"{name} differs from the single-GPU render"
+        parts, g2_cat = [], []
+        for r in range(world):
+            P_r = int(local[r]["means3D"].shape[0])
+            g2_r = SH.gather_grad2d(st, wss[r], recs[r], radii[r], P_r)
+            g2_cat.append(g2_r[:P_r])
+            parts.append(SH.backward_geom_local(st, local[r], recs[r], radii[r], g2_r))
+        assert util.rel_err(torch.cat(g2_cat).double().cpu().numpy(), g2d.double().cpu().numpy()) < 1e-5
+        for i, ref in enumerate(ref_grads):
+            if ref is None:
+                continue
+            got = torch.cat([p[i] for p in parts])
+            assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, i
+
+
 def test_gaussian_sharded_module_world1_matches_plain_rasterizer():
     """GaussianShardedRasterizer without a process group (world 1) runs the project -> records -> local chain-rule path end
     to end through autograd and must reproduce GaussianRasterizer."""
@@ -329,7 +388,8 @@ def test_gaussian_sharded_module_world1_matches_plain_rasterizer():
     st = util.settings_from(sgb, scene["cam"], dev)
     res = {}
     for name, mod in (("plain", sgb.GaussianRasterizer(st)), ("sharded", GaussianShardedRasterizer(st)),
-                      ("sharded_bounded", GaussianShardedRasterizer(st, capacity=sgb.InstanceCapacity()))):
+                      ("sharded_bounded", GaussianShardedRasterizer(st, capacity=sgb.InstanceCapacity())),
+                      ("sharded_p2p", GaussianShardedRasterizer(st, exchange="p2p"))):
         for rep in range(2 if name == "sharded_bounded" else 1):  # second call of the bounded module runs sync-free
             leaves = {k: scene[k].to(dev).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations", "semantics")}
             m2d = torch.zeros(20_000, 3, device=dev, requires_grad=True)
@@ -342,7 +402,7 @@ def test_gaussian_sharded_module_world1_matches_plain_rasterizer():
         mod.synchronize_capacity() if hasattr(mod, "synchronize_capacity") else None
         res[name] = dict(color=color.detach(), radii=radii, depth=depth.detach(), alpha=alpha.detach(), semantic=semantic.detach(),
                          grads={k: v.grad for k, v in leaves.items()}, m2d=m2d.grad)
-    for name in ("sharded", "sharded_bounded"):
+    for name in ("sharded", "sharded_bounded", "sharded_p2p"):
         for k in ("color", "radii", "depth", "alpha", "semantic"):
             assert torch.equal(res[name][k], res["plain"][k]), (name, k)
         for k, g in res["plain"]["grads"].items():

@@ -28,7 +28,7 @@ KEYS = ("means3D", "shs", "opacities", "scales", "rotations")
 GRAD_TOL = 5e-4
 
 
-def run_case(rank, world, dev, S, P, W, H, bounded):
+def run_case(rank, world, dev, S, P, W, H, bounded, exchange="nccl"):
     scene = synthetic.make_scene(P=P, width=W, height=H, sh_degree=3, seed=77, pose=True, semantics=S)
     st = util.settings_from(sgb, scene["cam"], dev)
     chunk = (P + world - 1) // world
@@ -61,7 +61,7 @@ def run_case(rank, world, dev, S, P, W, H, bounded):
     floor = max(util.rel_err(first[k].double().cpu().numpy(), full[k].grad.double().cpu().numpy()) for k in KEYS)
 
     cap = sgb.InstanceCapacity() if bounded else None
-    rast = GaussianShardedRasterizer(st, capacity=cap)
+    rast = GaussianShardedRasterizer(st, capacity=cap, exchange=exchange)
     worst = 0.0
     for rep in range(2 if bounded else 1):  # second pass of the bounded variant runs without any host sync
         loc = {k: scene[k][lo:hi].to(dev).requires_grad_(True) for k in KEYS}
@@ -101,9 +101,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ok = True
     try:
+        exchange = sys.argv[1] if len(sys.argv) > 1 else "nccl"
         for S, P, W, H, bounded in ((0, 200_003, 1280, 720, False), (2, 60_001, 800, 608, False), (0, 200_003, 1280, 720, True)):
-            worst, floor = run_case(rank, world, dev, S, P, W, H, bounded)
-            print(f"[rank {rank}/{world}] S={S} P={P} {W}x{H} bounded={bounded}: images bit-equal, worst grad rel err {worst:.2e} "
+            worst, floor = run_case(rank, world, dev, S, P, W, H, bounded, exchange)
+            print(f"[rank {rank}/{world}] exchange={exchange} S={S} P={P} {W}x{H} bounded={bounded}: images bit-equal, worst grad rel err {worst:.2e} "
                   f"(single-GPU run-to-run floor {floor:.2e})", flush=True)
     except AssertionError as e:
         ok = False
