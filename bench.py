@@ -53,7 +53,7 @@ def parse():
                          "this is the default for the timed region; the exact drop-in mode is timed beside it "
                          "(config.exact_mode_ms_per_step)")
     ap.add_argument("--exact", dest="sync_free", action="store_false", help="force the exact (read-back) mode")
-    ap.add_argument("--mp-mode", choices=["gaussian", "gaussian-p2p", "replicated"], default="gaussian",
+    ap.add_argument("--mp-mode", choices=["gaussian", "gaussian-p2p", "replicated"], default="gaussian-p2p",
                     help="N > 1 only. gaussian: every rank owns P/N Gaussians and a tile-row band (NCCL all-gather of records, "
                          "reduce-scatter of grad2d; GaussianShardedRasterizer).  gaussian-p2p: same partition, but records / grad2d rows "
                          "move by direct NVLink stores / loads to exactly the ranks that need them (exchange='p2p').  replicated: "
@@ -236,6 +236,20 @@ def main():
             chunk = (P + world - 1) // world
             rast = GaussianShardedRasterizer(make_settings(mod, cam, dev), capacity=capacity, chunk=chunk,
                                              exchange="p2p" if args.mp_mode == "gaussian-p2p" else "nccl")
+            if args.mp_mode == "gaussian-p2p":
+                # the peer-memory exchange needs torch symmetric memory (CUDA VMM handles shared between the ranks); if any
+                # rank cannot set it up, ALL ranks fall back to the NCCL exchange (measured 2.5 % slower at N = 8)
+                ok = 1
+                try:
+                    rast.workspace(dev)
+                except Exception as e:  # noqa: BLE001
+                    ok = 0
+                    print(f"[rank {rank}] peer workspace unavailable ({e!r}); falling back to the NCCL exchange", file=sys.stderr, flush=True)
+                flag = torch.tensor([ok], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    args.mp_mode = "gaussian"
+                    rast = GaussianShardedRasterizer(make_settings(mod, cam, dev), capacity=capacity, chunk=chunk, exchange="nccl")
         else:
             rast = ShardedGaussianRasterizer(make_settings(mod, cam, dev), capacity=capacity)
 
