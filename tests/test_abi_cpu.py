@@ -156,3 +156,63 @@ def test_instance_capacity_bookkeeping():
     cap.observe(10)          # never shrinks
     assert cap.capacity == 1500 + 4096
     cap.check()              # nothing pending: no-op
+
+
+def test_header_compiles_as_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/sgr.h is a plain-C header (no C++, no torch types) and the ctypes mirrors in _capi.py have the same size and
+    field offsets as the C structs — the boundary a cgo / JNI / ctypes binding would be written against."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields_frame = [f[0] for f in _capi.SgrFrame._fields_]
+    fields_peers = [f[0] for f in _capi.SgrPeers._fields_]
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "sgr.h"', 'int main(void) {',
+            '  printf("SgrFrame %zu\\n", sizeof(SgrFrame));', '  printf("SgrPeers %zu\\n", sizeof(SgrPeers));']
+    body += [f'  printf("SgrFrame.{f} %zu\\n", offsetof(SgrFrame, {f}));' for f in fields_frame]
+    body += [f'  printf("SgrPeers.{f} %zu\\n", offsetof(SgrPeers, {f}));' for f in fields_peers]
+    body += ['  printf("SGR_MAX_PEERS %d\\n", SGR_MAX_PEERS);', '  printf("SGR_ABI_VERSION %d\\n", SGR_ABI_VERSION);', '  return 0;', '}']
+    src.write_text("\n".join(body))
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["SgrFrame"]) == C.sizeof(_capi.SgrFrame) and int(out["SgrPeers"]) == C.sizeof(_capi.SgrPeers)
+    for f in fields_frame:
+        assert int(out[f"SgrFrame.{f}"]) == getattr(_capi.SgrFrame, f).offset, f
+    for f in fields_peers:
+        assert int(out[f"SgrPeers.{f}"]) == getattr(_capi.SgrPeers, f).offset, f
+    assert int(out["SGR_MAX_PEERS"]) == _capi.MAX_PEERS and int(out["SGR_ABI_VERSION"]) == _capi.ABI_VERSION
+
+
+def test_gaussian_sharded_entry_points_validate_before_touching_cuda():
+    """Argument errors of the multi-GPU entry points come back as SGR_EINVAL with a message — no CUDA call is made, so
+    this runs without a GPU."""
+    L = _capi.lib()
+    assert L.sgr_record_bytes() == 48
+    fr = _capi.SgrFrame()
+    fr.P, fr.width, fr.height, fr.D, fr.M = 100, 64, 64, 0, 0
+    fr.tan_fovx, fr.tan_fovy, fr.scale_modifier = 0.5, 0.5, 1.0
+    err = lambda: L.sgr_last_error().decode()
+    # sgr_project: camera pointers are checked first
+    assert L.sgr_project(C.byref(fr), None, None, None, None, None, None, None, None, None, None) == -1 and "camera" in err()
+    # sgr_forward_records: outputs, then radii
+    assert L.sgr_forward_records(C.byref(fr), None, None, None, None, None, None, None, 0, None, 0, _capi.ALLOC_FN(), None, None, None,
+                                 None, 0, -1, None) == -1 and "output image" in err()
+    # peer table validation
+    assert L.sgr_scatter_records(C.byref(fr), None, None, None, None) == -1 and "peers is NULL" in err()
+    pe = _capi.SgrPeers()
+    pe.world, pe.rank, pe.chunk = 0, 0, 100
+    assert L.sgr_scatter_records(C.byref(fr), C.byref(pe), None, None, None) == -1 and "bad peer table" in err()
+    pe.world = _capi.MAX_PEERS + 1
+    assert L.sgr_gather_grad2d(C.byref(fr), C.byref(pe), None, None, None, None) == -1 and "bad peer table" in err()
+    pe.world, pe.rank, pe.chunk = 2, 1, 50
+    assert L.sgr_scatter_records(C.byref(fr), C.byref(pe), None, None, None) == -1 and "smaller than the local" in err()
+    pe.chunk = 100
+    assert L.sgr_scatter_records(C.byref(fr), C.byref(pe), None, None, None) == -1 and "entry 0 is NULL" in err()
+
+
+def test_peer_workspace_layout_is_aligned_and_ordered():
+    from street_gaussians_b200.sharded import PeerWorkspace
+    st = sgb.GaussianRasterizationSettings(480, 640, 0.5, 0.4, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 3, torch.zeros(3), False, False)
+    P_total = 8 * 12_501
+    gb, ib, off_radii, off_grad, total = PeerWorkspace.layout(st, P_total, torch.device("cpu"))
+    assert gb >= P_total * 48 and off_radii >= gb and off_radii % 256 == 0
+    assert off_grad >= off_radii + 4 * P_total and off_grad % 256 == 0 and total == off_grad + 48 * P_total and ib > 0

@@ -48,6 +48,20 @@ def _worker(rank, world, port, layout, q):
         img[:, band_of_rows(H, rank, world, layout)] = 1.0
         (full,) = r.gather_images(img)
         assert torch.allclose(full, torch.ones(1, H, W))
+        # Gaussian-sharded module: same cyclic band, collective agreement on the per-rank slot count
+        from street_gaussians_b200.sharded import GaussianShardedRasterizer, cyclic_band
+        if layout == "cyclic":
+            g = GaussianShardedRasterizer(st, exchange="p2p")
+            assert g.band == cyclic_band(H, rank, world) and g.world == world and g.rank == rank and g.chunk is None
+            assert g.repartition(10 if rank == 0 else 17) == 17 and g.chunk_for(3) == 17
+        else:
+            g = GaussianShardedRasterizer(st, layout=layout, chunk=9)
+            assert g.chunk_for(5) == 9 and g.exchange == "nccl"
+            try:
+                GaussianShardedRasterizer(st, layout=layout, exchange="p2p")
+                raise AssertionError("p2p with a contiguous layout must be rejected")
+            except ValueError:
+                pass
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
