@@ -240,6 +240,7 @@ class PeerWorkspace:
             raise _capi.SgrError(f"peer exchange supports at most {_capi.MAX_PEERS} ranks, got {world}")
         self.geom_bytes, self.img_bytes, self.off_radii, self.off_grad, self.total = self.layout(settings, self.P_total, device)
         self.hdl = None
+        self.in_flight = False  # a differentiable forward has used the buffers and its backward has not run yet
         if _buffers is not None:  # single-process emulation: (my buffer, base pointers of all ranks' buffers)
             self.buf, ptrs = _buffers
         else:
@@ -327,6 +328,10 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         ws = owner.workspace(device) if owner.exchange == "p2p" else None
         sem_all = None
         if ws is not None:  # records go straight into the peers' gathered arrays over NVLink
+            if ws.in_flight:
+                raise _capi.SgrError("GaussianShardedRasterizer(exchange='p2p') owns ONE peer workspace: run backward() of the previous "
+                                     "forward (or call release_workspace()) before the next forward, or use one rasterizer per camera")
+            ws.in_flight = any(ctx.needs_input_grad)
             scatter_records(settings, ws, rec, radii, P)
             ws.barrier()
             st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
@@ -379,6 +384,7 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         if ws is not None:  # pull the partial rows of the own Gaussians from the ranks that rendered them
             ws.barrier()
             grad2d = gather_grad2d(settings, ws, rec, radii, P)
+            ws.in_flight = False  # stream order protects the buffers from here on: the next forward is enqueued after the gather
             if owner.world > 1 and S > 0:
                 gs_local = torch.empty((ctx.chunk, S), device=dev, dtype=torch.float32)
                 dist.reduce_scatter_tensor(gs_local.view(-1), g_sem.view(-1), op=dist.ReduceOp.SUM, group=owner.group)
@@ -448,6 +454,11 @@ class GaussianShardedRasterizer(nn.Module):
             else:
                 self._ws = PeerWorkspace.emulate(self.raster_settings, self.chunk, 1, device)[0]
         return self._ws
+
+    def release_workspace(self):
+        """Declare that the last differentiable forward will never be back-propagated (its graph was dropped)."""
+        if self._ws is not None:
+            self._ws.in_flight = False
 
     def chunk_for(self, P_local: int) -> int:
         if self.chunk is None:  # first forward: every rank is here together
