@@ -318,7 +318,8 @@ def peer_forward_state(ws: PeerWorkspace):
 
 class _GaussianShardedRasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp, settings, owner):
+    def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp, settings, owner,
+                differentiable=True):
         tensors = _local_tensors(means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp)
         device, P = means3D.device, int(means3D.shape[0])
         world, chunk, group = owner.world, owner.chunk_for(P), owner.group
@@ -331,7 +332,7 @@ class _GaussianShardedRasterize(torch.autograd.Function):
             if ws.in_flight:
                 raise _capi.SgrError("GaussianShardedRasterizer(exchange='p2p') owns ONE peer workspace: run backward() of the previous "
                                      "forward (or call release_workspace()) before the next forward, or use one rasterizer per camera")
-            ws.in_flight = any(ctx.needs_input_grad)
+            ws.in_flight = bool(differentiable)
             scatter_records(settings, ws, rec, radii, P)
             ws.barrier()
             st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
@@ -412,7 +413,7 @@ class _GaussianShardedRasterize(torch.autograd.Function):
             return t.reshape(shape).to(device=device, dtype=dtype)
 
         return (fit(g_means3D, 0), fit(g_means2D, 1), fit(g_sh, 2), fit(g_colors, 3), fit(g_sem[:P] if S > 0 else None, 4),
-                fit(g_opac, 5), fit(g_scales, 6), fit(g_rots, 7), fit(g_cov, 8), None, None)
+                fit(g_opac, 5), fit(g_scales, 6), fit(g_rots, 7), fit(g_cov, 8), None, None, None)
 
 
 class GaussianShardedRasterizer(nn.Module):
@@ -484,5 +485,6 @@ class GaussianShardedRasterizer(nn.Module):
         cov3D_precomp = e if cov3D_precomp is None else cov3D_precomp
         if semantics is None:
             semantics = torch.zeros((means3D.shape[0], 0), device=means3D.device)
-        return _GaussianShardedRasterize.apply(means3D, means2D, shs, colors_precomp, semantics, opacities, scales, rotations,
-                                               cov3D_precomp, self.raster_settings, self)
+        args = (means3D, means2D, shs, colors_precomp, semantics, opacities, scales, rotations, cov3D_precomp)
+        differentiable = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in args)
+        return _GaussianShardedRasterize.apply(*args, self.raster_settings, self, differentiable)
