@@ -332,7 +332,6 @@ class _GaussianShardedRasterize(torch.autograd.Function):
             if ws.in_flight:
                 raise _capi.SgrError("GaussianShardedRasterizer(exchange='p2p') owns ONE peer workspace: run backward() of the previous "
                                      "forward (or call release_workspace()) before the next forward, or use one rasterizer per camera")
-            ws.in_flight = bool(differentiable)
             scatter_records(settings, ws, rec, radii, P)
             ws.barrier()
             st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
@@ -364,6 +363,8 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         ctx.save_for_backward(rec, radii, alpha)
         radii_out = radii[:P]
         ctx.mark_non_differentiable(radii_out)
+        if ws is not None:
+            ws.in_flight = bool(differentiable)
         return color, radii_out, depth, alpha, semantic
 
     @staticmethod
