@@ -338,14 +338,12 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         else:
             st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
             radii_all = torch.empty((P_total,), device=device, dtype=torch.int32)
-        if ws is not None:
-            pass
-        elif world > 1:
-            dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1), group=group)
-            dist.all_gather_into_tensor(radii_all, radii, group=group)
-        else:
-            rec_all.copy_(rec)
-            radii_all.copy_(radii)
+            if world > 1:
+                dist.all_gather_into_tensor(rec_all.view(-1), rec.view(-1), group=group)
+                dist.all_gather_into_tensor(radii_all, radii, group=group)
+            else:
+                rec_all.copy_(rec)
+                radii_all.copy_(radii)
         if S > 0:
             sem_local = tensors["semantics"]
             if P < chunk:
