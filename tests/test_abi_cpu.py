@@ -216,3 +216,22 @@ def test_peer_workspace_layout_is_aligned_and_ordered():
     gb, ib, off_radii, off_grad, total = PeerWorkspace.layout(st, P_total, torch.device("cpu"))
     assert gb >= P_total * 48 and off_radii >= gb and off_radii % 256 == 0
     assert off_grad >= off_radii + 4 * P_total and off_grad % 256 == 0 and total == off_grad + 48 * P_total and ib > 0
+
+
+def test_peer_workspace_emulation_wires_the_peer_table():
+    """PeerWorkspace.emulate on CPU buffers: every rank's SgrPeers points at every buffer with the same section offsets,
+    and the torch views (gathered records inside geom, radii_all, grad2d) sit at those offsets."""
+    from street_gaussians_b200.sharded import PeerWorkspace
+    st = sgb.GaussianRasterizationSettings(96, 128, 0.5, 0.4, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3), False, False)
+    world, chunk = 3, 11
+    wss = PeerWorkspace.emulate(st, chunk, world, torch.device("cpu"))
+    bases = [ws.buf.data_ptr() for ws in wss]
+    for r, ws in enumerate(wss):
+        assert (ws.peers.world, ws.peers.rank, ws.peers.chunk) == (world, r, chunk) and ws.P_total == world * chunk and not ws.in_flight
+        assert ws.geom.data_ptr() == bases[r] and ws.radii_all.data_ptr() == bases[r] + ws.off_radii
+        assert ws.grad2d.data_ptr() == bases[r] + ws.off_grad and ws.grad2d.shape == (world * chunk, 12)
+        assert ws.radii_all.dtype == torch.int32 and ws.radii_all.shape == (world * chunk,)
+        for p in range(world):
+            assert ws.peers.records[p] == bases[p] and ws.peers.radii[p] == bases[p] + ws.off_radii
+            assert ws.peers.grad2d[p] == bases[p] + ws.off_grad
+        ws.barrier()  # no symmetric-memory handle in emulation: a no-op
