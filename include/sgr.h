@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGR_ABI_VERSION 3
+#define SGR_ABI_VERSION 4
 
 #define SGR_OK 0
 #define SGR_EINVAL (-1)   /* bad argument combination / shape                     */
@@ -74,6 +74,9 @@ typedef void *(*sgr_alloc_fn)(void *user, size_t nbytes);
 
 int sgr_abi_version(void);
 const char *sgr_last_error(void);
+/* Number of kernels of this library enqueued so far by the calling process (cub's internal sort / scan kernels are not
+ * included).  Diagnostic only — bench.py reports the delta over its timed region as `gpu_launches`.  No reference counterpart. */
+uint64_t sgr_launch_count(void);
 
 /* Sizes (bytes) of the caller-owned forward state.  geom: per-Gaussian records (reference GeometryState,
  * DGR/cuda_rasterizer/rasterizer_impl.h:21-37); img: per-pixel / per-tile state (ImageState, :46-52).

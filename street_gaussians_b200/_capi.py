@@ -8,9 +8,9 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsgr.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
-SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_state_sizes", "sgr_binning_bytes", "sgr_forward", "sgr_forward_bounded",
+SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_launch_count", "sgr_state_sizes", "sgr_binning_bytes", "sgr_forward", "sgr_forward_bounded",
            "sgr_forward_status", "sgr_forward_status_async", "sgr_backward_blend",
            "sgr_backward_geom", "sgr_backward", "sgr_mark_visible", "sgr_visible_filter", "sgr_knn_scratch_bytes",
            "sgr_knn_mean_dist2", "sgr_record_bytes", "sgr_project", "sgr_forward_records",
@@ -57,6 +57,8 @@ def lib():
     if L.sgr_abi_version() != ABI_VERSION:
         raise SgrError(f"libsgr.so ABI version {L.sgr_abi_version()} != expected {ABI_VERSION}; rebuild")
     L.sgr_last_error.restype = C.c_char_p
+    L.sgr_launch_count.restype = C.c_uint64
+    L.sgr_launch_count.argtypes = []
     L.sgr_state_sizes.restype = C.c_int
     L.sgr_state_sizes.argtypes = [C.POINTER(SgrFrame), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.sgr_binning_bytes.restype = C.c_size_t

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) count_tiles_kernel(const FrameDev f, cons
 }
 cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
+	count_launch();
 	count_tiles_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.depth_key, g.iota);
 	return cudaGetLastError();
 }
@@ -113,7 +114,13 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 	uint32_t end = offsets[tc];
 	uint32_t off = tc == 0 ? 0u : offsets[tc - 1];
 	if (t >= f.P) off = end;
-	if (end > cap) end = off;  // bounded mode: a Gaussian whose range does not fit the caller's capacity emits nothing
+	// bounded mode: a Gaussian whose range does not fit the caller's capacity emits nothing.  BOTH ends are clamped so that
+	// warp_first / warp_last (taken from lanes 0 / 31 below) never address past `cap`, even when every lane of the warp
+	// overflows: the staged flush then covers at most [warp_first, cap), and pad_keys_kernel rewrites [emitted, cap).
+	if (end > cap) {
+		off = min(off, cap);
+		end = off;
+	}
 	if (t < f.P) {
 		gidx = perm[t];
 		if (end > off) {
@@ -234,6 +241,7 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 	if (e != cudaSuccess) return e;
 	if (f.P == 0) return cudaSuccess;
 	const uint32_t cap32 = bounded ? (uint32_t)cap : 0xffffffffu;
+	count_launch();
 	count_status_kernel<<<1, 1, 0, st>>>(g.offsets, f.P, cap32, g.big_count);
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if (bounded) R = cap;  // every pass below runs over the caller's capacity; the padding carries the largest key
@@ -246,20 +254,28 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 	const int sort_bits = bounded ? (ntile <= 65535 ? 16 : 32) : bits_for(ntile);
 	if (ntile <= 65535 || (!bounded && ntile <= 65536)) {  // 16-bit tile ids (the key arrays are allocated for 32-bit ids either way)
 		uint16_t *kin = reinterpret_cast<uint16_t *>(b.keys_in), *kout = reinterpret_cast<uint16_t *>(b.keys_out);
+		count_launch();
 		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32);
+		count_launch();
 		emit_big_kernel<uint16_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32);
+		if (bounded) count_launch();
 		if (bounded) pad_keys_kernel<uint16_t><<<npad_blk, 256, 0, st>>>(kin, b.vals_in, cap32, g.big_count);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, kin, kout, b.vals_in, b.vals_out, R, 0, sort_bits, st);
 		if (e != cudaSuccess) return e;
+		count_launch();
 		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 256 * kRangeKeysPerThread - 1) / (256 * kRangeKeysPerThread)), 256, 0, st>>>(R, kout, img.ranges, (uint32_t)ntile);
 	} else {
+		count_launch();
 		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
+		count_launch();
 		emit_big_kernel<uint32_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
+		if (bounded) count_launch();
 		if (bounded) pad_keys_kernel<uint32_t><<<npad_blk, 256, 0, st>>>(b.keys_in, b.vals_in, cap32, g.big_count);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 		e = cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, R, 0, sort_bits, st);
 		if (e != cudaSuccess) return e;
+		count_launch();
 		tile_ranges_kernel<uint32_t><<<(unsigned)((R + 256 * kRangeKeysPerThread - 1) / (256 * kRangeKeysPerThread)), 256, 0, st>>>(R, b.keys_out, img.ranges, (uint32_t)ntile);
 	}
 	return cudaGetLastError();

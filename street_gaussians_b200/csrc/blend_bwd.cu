@@ -303,6 +303,7 @@ cudaError_t launch_blend_bwd(const FrameDev &f, GeomView g, BinView b, ImgView i
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
 	const dim3 grid(f.gx, rows);
+	count_launch();
 #define SGR_LAUNCH_BWD(SCH)                                                                                                      \
 	blend_bwd_kernel<SCH><<<grid, 256, 0, st>>>(f, img.ranges, b.vals_out, g.rec, semantics, img.n_contrib, img.tile_max_contrib, \
 	                                            out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, dL_dsem, grad2d, dL_dsemantics)

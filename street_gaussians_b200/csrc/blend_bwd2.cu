@@ -252,14 +252,9 @@ cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView 
 	if (e != cudaSuccess) return e;
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
-	static bool configured[64] = {};  // the attribute is per device: one flag per ordinal
-	int dev = 0;
-	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		e = cudaFuncSetAttribute(blend_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
-		if (e != cudaSuccess) return e;
-		if (dev >= 0 && dev < 64) configured[dev] = true;
-	}
+	static std::atomic<uint64_t> configured{0};
+	if ((e = ensure_dynamic_smem(blend_bwd2_kernel, (int)kSmem2, configured)) != cudaSuccess) return e;
+	count_launch();
 	blend_bwd2_kernel<<<dim3(f.gx, rows), 256, kSmem2, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, img.tile_max_contrib, out_alpha,
 	                                                         dL_dcolor, dL_ddepth, dL_dalpha, grad2d);
 	return cudaGetLastError();

@@ -159,6 +159,7 @@ cudaError_t launch_blend_fwd(const FrameDev &f, GeomView g, BinView b, ImgView i
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
 	const dim3 grid(f.gx, rows);
+	count_launch();
 #define SGR_LAUNCH_FWD(SCH, ch0, only)                                                                                        \
 	blend_fwd_kernel<SCH><<<grid, 256, 0, st>>>(f, img.ranges, b.vals_out, g.rec, semantics, img.n_contrib,                     \
 	                                            img.tile_max_contrib, out_color, out_depth, out_alpha, out_sem, ch0, only)
@@ -172,7 +173,10 @@ cudaError_t launch_blend_fwd(const FrameDev &f, GeomView g, BinView b, ImgView i
 		SGR_LAUNCH_FWD(16, 0, 0);
 	else {
 		SGR_LAUNCH_FWD(32, 0, 0);
-		for (int ch0 = 32; ch0 < f.S; ch0 += 32) SGR_LAUNCH_FWD(32, ch0, 1);  // further channel chunks: semantics only
+		for (int ch0 = 32; ch0 < f.S; ch0 += 32) {  // further channel chunks: semantics only
+			count_launch();
+			SGR_LAUNCH_FWD(32, ch0, 1);
+		}
 	}
 #undef SGR_LAUNCH_FWD
 	return cudaGetLastError();

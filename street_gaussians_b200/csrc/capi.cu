@@ -10,6 +10,21 @@
 namespace sgr {
 
 static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_kernel_launches{0};
+
+// cub's temp-storage size queries (two per carve_geom, two per carve_bin) walk cub's dispatch layer every time; every C-ABI
+// call carves its state, so the answers are memoised per thread for the last few problem sizes.
+template <typename F>
+static size_t memo_bytes(int64_t n, F compute) {
+	struct Slot { int64_t n; size_t bytes; };
+	static thread_local Slot slots[4] = {{-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}};
+	static thread_local unsigned next = 0;
+	for (const Slot &s : slots)
+		if (s.n == n) return s.bytes;
+	const size_t b = compute(n);
+	slots[next++ & 3u] = Slot{n, b};
+	return b;
+}
 
 static int fail(int code, const char *fmt, ...) {
 	va_list ap;
@@ -39,7 +54,7 @@ GeomView carve_geom(void *base, int P) {
 	g.offsets = take<uint32_t>(p, n);
 	g.big_list = take<uint32_t>(p, n);
 	g.big_count = take<uint32_t>(p, 64);
-	g.temp_bytes = geom_temp_bytes(P);
+	g.temp_bytes = memo_bytes((int64_t)P, [](int64_t n) { return geom_temp_bytes((int)n); });
 	g.temp = take<char>(p, g.temp_bytes);
 	g.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
 	return g;
@@ -62,7 +77,7 @@ BinView carve_bin(void *base, int64_t R) {
 	b.keys_out = take<uint32_t>(p, n);
 	b.vals_in = take<uint32_t>(p, n);
 	b.vals_out = take<uint32_t>(p, n);
-	b.sort_temp_bytes = sort_temp_bytes(R);
+	b.sort_temp_bytes = memo_bytes(R, [](int64_t n) { return sort_temp_bytes(n); });
 	b.sort_temp = take<char>(p, b.sort_temp_bytes);
 	b.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
 	return b;
@@ -145,6 +160,7 @@ using namespace sgr;
 extern "C" {
 
 int sgr_abi_version(void) { return SGR_ABI_VERSION; }
+uint64_t sgr_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 const char *sgr_last_error(void) { return g_err; }
 
 int sgr_state_sizes(const SgrFrame *frame, size_t *geom_bytes, size_t *img_bytes) {

@@ -149,15 +149,20 @@ __global__ void __launch_bounds__(256) knn_search_kernel(int P, const float4 *__
 cudaError_t launch_knn(int P, const float *points, float *out, void *scratch, size_t scratch_bytes, cudaStream_t st) {
 	(void)scratch_bytes;
 	KnnView v = carve_knn(scratch, P);
+	count_launch();
 	knn_init_bounds<<<1, 32, 0, st>>>(v.bounds);
 	const int nblk = (P + 255) / 256;
+	count_launch();
 	knn_bounds_kernel<<<min(nblk, 1184), 256, 0, st>>>(P, points, v.bounds);
+	count_launch();
 	knn_morton_kernel<<<nblk, 256, 0, st>>>(P, points, v.bounds, v.codes, v.idx);
 	size_t bytes = v.sort_temp_bytes;
 	cudaError_t e = cub::DeviceRadixSort::SortPairs(v.sort_temp, bytes, v.codes, v.codes_sorted, v.idx, v.idx_sorted, P, 0, 30, st);
 	if (e != cudaSuccess) return e;
 	const int nbox = (P + kBox - 1) / kBox;
+	count_launch();
 	knn_boxes_kernel<<<nbox, kBox, 0, st>>>(P, points, v.idx_sorted, v.sorted_pts, v.boxes);
+	count_launch();
 	knn_search_kernel<<<nblk, 256, 0, st>>>(P, v.sorted_pts, v.boxes, out);
 	return cudaGetLastError();
 }

@@ -75,12 +75,14 @@ __global__ void __launch_bounds__(256) gather_grad2d_kernel(const FrameDev f, co
 
 cudaError_t launch_scatter_records(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, cudaStream_t st) {
 	if (pt.chunk == 0) return cudaSuccess;
+	count_launch();
 	scatter_records_kernel<<<(unsigned)((pt.chunk + 255) / 256), 256, 0, st>>>(f, pt, rec, radii);
 	return cudaGetLastError();
 }
 cudaError_t launch_gather_grad2d(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, float *out,
                                  cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
+	count_launch();
 	gather_grad2d_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, pt, rec, radii, out);
 	return cudaGetLastError();
 }

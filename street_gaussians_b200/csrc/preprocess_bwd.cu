@@ -345,19 +345,15 @@ cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const
 	const bool staged = shs != nullptr && f.M <= 16;  // rows of up to 48 floats fit the padded smem row
 	if (staged) {
 		const size_t smem = (size_t)8 * 32 * kShRow * sizeof(float);  // 50,176 B: above the 48 KB static limit -> opt in
-		static bool configured[64] = {};  // the attribute is per device: one flag per ordinal
-		int dev = 0;
-		cudaError_t e = cudaGetDevice(&dev);
+		static std::atomic<uint64_t> configured{0};
+		cudaError_t e = ensure_dynamic_smem(preprocess_bwd_kernel<true>, (int)smem, configured);
 		if (e != cudaSuccess) return e;
-		if (dev < 0 || dev >= 64 || !configured[dev]) {
-			e = cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess) return e;
-			if (dev >= 0 && dev < 64) configured[dev] = true;
-		}
+		count_launch();
 		preprocess_bwd_kernel<true><<<(f.P + 255) / 256, 256, smem, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
 		                                                                  radii, g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 		                                                                  dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
 	} else {
+		count_launch();
 		preprocess_bwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
 		                                                               radii, g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 		                                                               dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);

@@ -234,6 +234,7 @@ cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const
                                   const float *opacities, const float *scales, const float *rotations,
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
+	count_launch();
 	preprocess_fwd_kernel<true><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
 	                                                                  cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
 	return cudaGetLastError();
@@ -242,6 +243,7 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
                            const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp,
                            int32_t *radii, GaussRec *rec, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
+	count_launch();
 	preprocess_fwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
 	                                                                   cov3D_precomp, radii, rec, nullptr, nullptr, nullptr);
 	return cudaGetLastError();
@@ -249,11 +251,13 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
+	count_launch();
 	filter_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, scales, rotations, cov3D_precomp, radii, means2D);
 	return cudaGetLastError();
 }
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st) {
 	if (P == 0) return cudaSuccess;
+	count_launch();
 	mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, view, present);
 	return cudaGetLastError();
 }

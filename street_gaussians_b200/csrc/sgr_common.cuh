@@ -10,6 +10,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
 #include "../../include/sgr.h"
 
 #define SGR_TILE 16            // tile edge in pixels (reference BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:17-18)
@@ -56,6 +58,26 @@ struct BinView {
 };
 
 static inline size_t align_up(size_t v, size_t a = SGR_ALIGN) { return (v + a - 1) / a * a; }
+
+// Number of kernels of THIS library enqueued so far by the process (cub's internal kernels are not counted); read through
+// sgr_launch_count() — bench.py reports the delta over its timed region as `gpu_launches`.
+extern std::atomic<uint64_t> g_kernel_launches;
+static inline void count_launch(unsigned n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device).  `done` holds one bit per device ordinal; the
+// check-then-set is idempotent (two threads racing both set the same attribute to the same value), and the bit is published
+// with release/acquire ordering, so the library stays thread-safe without a lock.
+template <typename K>
+static inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<uint64_t> &done) {
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	const bool tracked = dev >= 0 && dev < 64;
+	if (tracked && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+	e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e == cudaSuccess && tracked) done.fetch_or(1ull << dev, std::memory_order_release);
+	return e;
+}
 
 // Column-major 3x3 (m[c][r]) with the product written as a left-associated sum of three products.  The reference
 // uses glm::mat3, whose operator* has this exact algebraic form; keeping the form lets nvcc contract mul+add

@@ -32,16 +32,23 @@ __device__ __forceinline__ float fast_div(float x, float y) { return __fdividef(
 // x-extent [xmin, xmax] (relative to the centre) of {ellipse q <= qmax} ∩ {uy0 <= y <= uy1}; false if empty.
 // Requires a finite qmax and a positive-definite conic (make_cull guarantees both when qmax is finite).
 struct EllipseAux {
-	float det_over_a, inv_a, xext, yhi;  // det/a, 1/a; extreme |x| of the ellipse, reached at y = -/+ yhi
+	float det, det_over_a, inv_a, xext, yhi;  // det, det/a, 1/a; extreme |x| of the ellipse, reached at y = -/+ yhi
 };
 __device__ __forceinline__ EllipseAux ellipse_aux(const CullParams cp) {
 	EllipseAux e;
 	const float det = cp.a * cp.c - cp.b * cp.b;
+	e.det = det;
 	e.inv_a = fast_div(1.0f, cp.a);
 	e.det_over_a = det * e.inv_a;
 	e.xext = fast_sqrt(fast_div(cp.qmax * cp.c, det));
 	e.yhi = -cp.b * fast_div(e.xext, cp.c);
 	return e;
+}
+// disc = b^2 y^2 - a (c y^2 - qmax) = a qmax - det y^2, written with ONE rounding of the cancelling part (det is taken once
+// from the conic): the expanded form loses O(1) absolute accuracy for thin diagonal splats far from the strip.  Explicit
+// fmaf / __fmul_rn so that the count and emit instantiations cannot be contracted differently by nvcc.
+__device__ __forceinline__ float strip_disc(const CullParams cp, const EllipseAux ea, float y) {
+	return fmaxf(0.f, fmaf(-ea.det, __fmul_rn(y, y), __fmul_rn(cp.a, cp.qmax)));
 }
 __device__ __forceinline__ bool strip_xrange(const CullParams cp, const EllipseAux ea, float uy0, float uy1, float &xmin, float &xmax) {
 	const float yc = fminf(fmaxf(0.f, uy0), uy1);             // strip row closest to the centre
@@ -50,12 +57,12 @@ __device__ __forceinline__ bool strip_xrange(const CullParams cp, const EllipseA
 	xmin = -ea.xext;
 	if (ea.yhi < uy0 || ea.yhi > uy1) {
 		const float y = fminf(fmaxf(ea.yhi, uy0), uy1);
-		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
+		const float disc = strip_disc(cp, ea, y);
 		xmax = (-cp.b * y + fast_sqrt(disc)) * ea.inv_a;
 	}
 	if (-ea.yhi < uy0 || -ea.yhi > uy1) {
 		const float y = fminf(fmaxf(-ea.yhi, uy0), uy1);
-		const float disc = fmaxf(0.f, cp.b * cp.b * y * y - cp.a * (cp.c * y * y - cp.qmax));
+		const float disc = strip_disc(cp, ea, y);
 		xmin = (-cp.b * y - fast_sqrt(disc)) * ea.inv_a;
 	}
 	return true;

@@ -104,33 +104,41 @@ class InstanceCapacity:
 
     def __init__(self, headroom: float = 1.25, initial: Optional[int] = None):
         self.headroom, self.capacity = float(headroom), (int(initial) if initial else None)
-        self._pending = []  # (pinned uint32[2], cuda event)
+        self._pending = []  # (pinned int32[2], cuda event) in submission order
+        self._pool = []     # pinned status words ready for reuse: no pin_memory() (a cudaHostAlloc) inside the steady-state step
 
     def observe(self, R: int):
         want = int(R * self.headroom) + 4096
         if self.capacity is None or want > self.capacity:
             self.capacity = want
 
+    def status_word(self) -> torch.Tensor:
+        """A pinned int32[2] for sgr_forward_status_async; recycled once its frame has been checked."""
+        return self._pool.pop() if self._pool else torch.zeros(2, dtype=torch.int32).pin_memory()
+
     def track(self, host_status: torch.Tensor, event):
         self._pending.append((host_status, event))
 
     def check(self, wait: bool = False):
-        keep = []
-        for host_status, ev in self._pending:
+        """Examine the frames whose status has arrived (all of them with wait=True).  Raises on the FIRST overflowed frame
+        after growing the capacity; the frames after it stay pending, so a later call still reports them.  An overflowed
+        frame was rendered incomplete: call check(wait=True) (GaussianRasterizer.synchronize_capacity()) before the
+        optimiser step when that matters, and re-render."""
+        pending, self._pending = self._pending, []
+        for i, (host_status, ev) in enumerate(pending):
             if wait:
                 ev.synchronize()
             if not ev.query():
-                keep.append((host_status, ev))
+                self._pending.append((host_status, ev))
                 continue
             R, overflow = int(host_status[0]), int(host_status[1])
+            self._pool.append(host_status)
+            old = self.capacity
+            self.observe(R)
             if overflow:
-                old = self.capacity
-                self.observe(R)
-                self._pending = keep
+                self._pending.extend(pending[i + 1:])
                 raise _capi.SgrError(f"instance capacity {old} overflowed (frame needed {R}); capacity raised to {self.capacity} — "
                                      "re-render that frame")
-            self.observe(R)
-        self._pending = keep
 
 
 def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
@@ -190,7 +198,7 @@ def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rot
                                        _ptr(semantic), _ptr(radii), _ptr(st.geom), gb.value, _ptr(st.img), ib.value, _ptr(st.binning), nbytes,
                                        cap, _stream(device))
             _capi.check(rc, "sgr_forward_bounded")
-            host_status = torch.zeros(2, dtype=torch.int32).pin_memory()
+            host_status = capacity.status_word()
             rc = L.sgr_forward_status_async(C.byref(fr), _ptr(st.geom), C.c_void_p(host_status.data_ptr()), _stream(device))
             _capi.check(rc, "sgr_forward_status_async")
             ev = torch.cuda.Event()
@@ -284,17 +292,26 @@ class _RasterizeGaussians(torch.autograd.Function):
                                            raster_settings.campos, raster_settings.prefiltered, raster_settings.debug))
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
             raise
-        ctx.raster_settings, ctx.band, ctx.state, ctx.tensors, ctx.grad_reduce = raster_settings, band, st, tensors, grad_reduce
+        ctx.raster_settings, ctx.band, ctx.state, ctx.grad_reduce = raster_settings, band, st, grad_reduce
         ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype)
                            for t in (means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp))
-        ctx.save_for_backward(radii, alpha)
+        # The fp32-contiguous inputs go through save_for_backward like the reference's (DGR __init__.py:101), so autograd's
+        # version counters catch an in-place update of a parameter between forward and backward instead of silently
+        # differentiating the mutated values.
+        ctx.tensor_keys = None if tensors is None else tuple(k for k, v in tensors.items() if v is not None)
+        ctx.tensor_none = None if tensors is None else tuple(k for k, v in tensors.items() if v is None)
+        ctx.save_for_backward(radii, alpha, *([] if tensors is None else [tensors[k] for k in ctx.tensor_keys]))
         ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha, semantic
 
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha, grad_semantic):
-        radii, alpha = ctx.saved_tensors
-        st, tensors, settings, band = ctx.state, ctx.tensors, ctx.raster_settings, ctx.band
+        radii, alpha, *saved = ctx.saved_tensors
+        tensors = None
+        if ctx.tensor_keys is not None:
+            tensors = dict(zip(ctx.tensor_keys, saved))
+            tensors.update({k: None for k in ctx.tensor_none})
+        st, settings, band = ctx.state, ctx.raster_settings, ctx.band
         shapes = ctx.shapes
 
         def zeros_like_input(i):

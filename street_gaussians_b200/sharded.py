@@ -190,7 +190,7 @@ def forward_records(settings: GaussianRasterizationSettings, band: Optional[Tile
                                    _ptr(st.binning) if bounded else None, nbytes, cap, _stream(device))
         _capi.check(rc, "sgr_forward_records")
         if bounded:
-            host_status = torch.zeros(2, dtype=torch.int32).pin_memory()
+            host_status = capacity.status_word()
             rc = L.sgr_forward_status_async(C.byref(fr), _ptr(st.geom), C.c_void_p(host_status.data_ptr()), _stream(device))
             _capi.check(rc, "sgr_forward_status_async")
             ev = torch.cuda.Event()

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_sizes_no_gpu():
     L = _capi.lib()
-    assert L.sgr_abi_version() == 3
+    assert L.sgr_abi_version() == _capi.ABI_VERSION
     fr = _capi.SgrFrame()
     fr.P, fr.width, fr.height, fr.D, fr.M = 1000, 640, 480, 3, 16
     fr.tan_fovx, fr.tan_fovy, fr.scale_modifier = 0.5, 0.4, 1.0

@@ -39,16 +39,21 @@ def test_oracle_matches_reference_golden(path):
     ref = {k[4:]: z[k] for k in z.files if k.startswith("ref_")}
     assert (res["radii"] == ref["radii"]).all()
     npx = scene["cam"]["image_height"] * scene["cam"]["image_width"]
-    for k in ("color", "depth", "alpha", "semantic"):
-        if k in ref and ref[k].size:
-            d = np.abs(res[k].astype(np.float64) - ref[k])
-            scale = max(1.0, float(np.abs(ref[k]).max())) if k == "depth" else 1.0  # depth is un-normalised metres
-            # hard thresholds (alpha < 1/255, T < 1e-4) may flip on isolated pixels: plain C vs FMA-contracted GPU code
-            assert (d > 1e-4 * scale).sum() <= max(3, npx // 2000), (k, int((d > 1e-4 * scale).sum()), float(d.max()))
-            assert np.median(d) < 1e-6 * scale
+    # Flip protocol: every pixel above 1e-4 is listed and must be explained by <= 2 flips of the reference's hard
+    # per-pair thresholds (plain C vs nvcc's FMA-contracted arithmetic); the count stays tiny.
+    geom = util.run_oracle(scene, backward=False, use_colors_precomp=use_cp)["_fw"].geom()
+    vis = ref["radii"] > 0
+    maxv = dict(color=float(geom["rgb"][vis].max()) + float(np.abs(z["bg"]).max()), depth=float(geom["depth"][vis].max()), alpha=1.0)
+    if "semantic" in ref and ref["semantic"].size:
+        maxv["semantic"] = float(np.abs(z["in_semantics"]).max())
+    names = [k for k in ("color", "depth", "alpha", "semantic") if k in ref and ref[k].size]
+    off = util.check_forward_flip_protocol(res, ref, maxv, names=names, max_pixels=max(3, npx // 5000))
+    if off:
+        print("threshold-flip pixels:", off)
+    # gradients: the north-star's 1e-3 bar, oracle vs the compiled reference (measured: <= 5.3e-4 on these fixtures)
     for k, v in ref.items():
         if k.startswith("g_") and res.get(k) is not None and v.size:
-            assert util.rel_err(res[k], v) < 3e-3, (k, util.rel_err(res[k], v))
+            assert util.rel_err(res[k], v) < 1e-3, (k, util.rel_err(res[k], v))
 
 
 def test_golden_fixtures_present():

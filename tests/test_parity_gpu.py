@@ -27,8 +27,25 @@ FWD_TOL, GRAD_TOL = 1e-4, 1e-3
 ORACLE_GRAD_TOL = 5e-3
 
 
-def assert_forward_close(res, ref, npx, allow_flips=0):
+def oracle_maxv(fw, scene):
+    """Largest blendable value per output image, for the threshold-flip bound of util.check_forward_flip_protocol."""
+    g = fw.geom()
+    vis = fw.radii > 0
+    m = dict(color=float(g["rgb"][vis].max()) + float(scene["cam"]["bg"].abs().max()) if vis.any() else 1.0,
+             depth=float(g["depth"][vis].max()) if vis.any() else 1.0, alpha=1.0)
+    if "semantics" in scene:
+        m["semantic"] = float(scene["semantics"].abs().max())
+    return m
+
+
+def assert_forward_close(res, ref, npx, allow_flips=0, maxv=None):
     assert (np.asarray(res["radii"]) == np.asarray(ref["radii"])).all(), "radii must match exactly"
+    if maxv is not None:  # flip protocol (SURVEY.md §7): list every pixel > 1e-4, each must be explained by <= 2 threshold flips
+        names = [k for k in ("color", "depth", "alpha", "semantic") if k in ref and np.asarray(ref[k]).size]
+        off = util.check_forward_flip_protocol(res, ref, maxv, names=names, max_pixels=allow_flips)
+        if off:
+            print("threshold-flip pixels:", off[:20])
+        return
     for k in ("color", "depth", "alpha", "semantic"):
         if k in ref and np.asarray(ref[k]).size:
             d = np.abs(np.asarray(res[k], np.float64) - np.asarray(ref[k], np.float64))
@@ -69,9 +86,9 @@ def test_cuda_vs_oracle_small(name, kw, opts):
     scene = synthetic.make_scene(**kw)
     mine = util.run_api(sgb, scene)
     orc = util.run_oracle(scene)
-    orc.pop("_fw")
+    maxv = oracle_maxv(orc.pop("_fw"), scene)
     npx = kw["width"] * kw["height"]
-    assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx))
+    assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx), maxv=maxv)
     assert_grads_close(mine, orc, tol=ORACLE_GRAD_TOL)
 
 
@@ -102,9 +119,9 @@ def test_smoke_script_replay_vs_oracle():
         scene = synthetic.smoke_script_scene(num_points=3000, width=311, height=94, seed=3, semantics=S)
         mine = util.run_api(sgb, scene)
         orc = util.run_oracle(scene)
-        orc.pop("_fw")
+        maxv = oracle_maxv(orc.pop("_fw"), scene)
         npx = 311 * 94
-        assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx))
+        assert_forward_close(mine, orc, npx, allow_flips=flips_allowed(npx), maxv=maxv)
         assert_grads_close(mine, orc, tol=ORACLE_GRAD_TOL)
 
 
@@ -124,6 +141,32 @@ def test_cuda_vs_reference_golden(path):
 
 def test_golden_present():
     assert len(GOLDEN) >= 1
+
+
+def test_callsite_replay_vs_reference():
+    """SURVEY.md §8 a13, GPU half.  tests/golden/callsite/render_kernel.npz is the rasterizer call that the reference's UNMODIFIED
+    StreetGaussianRenderer.render_kernel made for a real StreetGaussianModel (recorded on the build container by
+    tests/golden/make_callsite_golden.py; tests/test_callsite_cpu.py pins the Python surface there).  Here the same call goes
+    through the compiled reference (oracle/_ref) and through this library: outputs and every .grad — including all three
+    columns of viewspace_points.grad — must agree to the north-star tolerances.  Without oracle/_ref the CPU oracle stands in."""
+    from test_oracle_cpu import scene_from_npz
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "callsite", "render_kernel.npz")
+    scene = scene_from_npz(np.load(path))
+    H, W = scene["cam"]["image_height"], scene["cam"]["image_width"]
+    g = torch.Generator().manual_seed(1)
+    for k, c in (("grad_color", 3), ("grad_depth", 1), ("grad_alpha", 1)):
+        scene[k] = torch.randn(c, H, W, generator=g) / (H * W)
+    mine = util.run_api(sgb, scene)
+    assert mine["g_means2D"].shape == (scene["means3D"].shape[0], 3) and np.abs(mine["g_means2D"][:, 2]).max() > 0
+    if util.ref_available():
+        r = util.run_api(util.load_ref(), scene)
+        assert_forward_close(mine, r, H * W, allow_flips=0)
+        assert_grads_close(mine, r, tol=GRAD_TOL)
+    else:
+        orc = util.run_oracle(scene)
+        maxv = oracle_maxv(orc.pop("_fw"), scene)
+        assert_forward_close(mine, orc, H * W, allow_flips=flips_allowed(H * W), maxv=maxv)
+        assert_grads_close(mine, orc, tol=ORACLE_GRAD_TOL)
 
 
 needs_ref = pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref (compiled reference) did not travel to this box")

@@ -132,3 +132,34 @@ def compare(res, ref, keys=None, verbose=True, tag=""):
     if verbose:
         print(tag, {k: (f"{v:.3e}" if isinstance(v, float) else v) for k, v in out.items()})
     return out
+
+
+def flip_bound(scene_or_maxc, bg=None):
+    """SURVEY.md §7 'Discontinuities' (ii)/(iv): ONE flipped hard threshold changes a pixel by at most
+         alpha<1/255 skip   : (1/255) * T * |c_i - C_behind|   <= (1/255) * (max|c| + max|bg|)
+         T(1-alpha)<1e-4 stop: 1e-4 * (max|c| + max|bg|)
+    where max|c| is the largest per-Gaussian colour (or depth / feature) value that can be blended."""
+    return (1.0 / 255.0 + 1e-4) * float(scene_or_maxc + (0.0 if bg is None else bg))
+
+
+def check_forward_flip_protocol(res, ref, max_value, tol=1e-4, max_flips_per_pixel=2, max_pixels=None, names=("color",)):
+    """The parity protocol of SURVEY.md §7: enumerate EVERY pixel whose difference exceeds `tol` and require each to be explained
+    by at most `max_flips_per_pixel` threshold flips (flip_bound); all other pixels are within `tol`.  Returns the offender list
+    [(name, channel, y, x, diff)] so callers can print / count it.  `max_value[name]` = largest blendable value of that image."""
+    offenders = []
+    for name in names:
+        a, b = np.asarray(res[name], np.float64), np.asarray(ref[name], np.float64)
+        if b.size == 0:
+            continue
+        d = np.abs(a - b)
+        scale = max(1.0, float(np.abs(b).max())) if name == "depth" else 1.0
+        idx = np.argwhere(d > tol * scale)
+        bound = max_flips_per_pixel * flip_bound(max_value[name]) * 1.05
+        for c, y, x in idx:
+            assert d[c, y, x] <= bound, f"{name}[{c},{y},{x}] differs by {d[c, y, x]:.3e} > {max_flips_per_pixel} threshold flips ({bound:.3e})"
+            offenders.append((name, int(c), int(y), int(x), float(d[c, y, x])))
+        assert np.median(d) <= 1e-6 * scale, (name, float(np.median(d)))
+    if max_pixels is not None:
+        px = {(o[2], o[3]) for o in offenders}
+        assert len(px) <= max_pixels, f"{len(px)} pixels above {tol}: {offenders[:10]}"
+    return offenders
