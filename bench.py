@@ -53,11 +53,14 @@ def parse():
                          "this is the default for the timed region; the exact drop-in mode is timed beside it "
                          "(config.exact_mode_ms_per_step)")
     ap.add_argument("--exact", dest="sync_free", action="store_false", help="force the exact (read-back) mode")
-    ap.add_argument("--mp-mode", choices=["gaussian", "gaussian-p2p", "replicated"], default="gaussian-p2p",
+    ap.add_argument("--mp-mode", choices=["gaussian", "gaussian-p2p", "gaussian-p2p-staged", "gaussian-p2p-allgather", "replicated"], default="gaussian-p2p",
                     help="N > 1 only. gaussian: every rank owns P/N Gaussians and a tile-row band (NCCL all-gather of records, "
                          "reduce-scatter of grad2d; GaussianShardedRasterizer).  gaussian-p2p: same partition, but records / grad2d rows "
-                         "move by direct NVLink stores / loads to exactly the ranks that need them (exchange='p2p').  replicated: "
-                         "parameters replicated, tile rows sharded, one all-reduce (ShardedGaussianRasterizer)")
+                         "move by direct NVLink stores / loads to exactly the ranks that need them (exchange='p2p'), one C-ABI call per "
+                         "forward / backward (sgr_sharded_forward / sgr_sharded_backward).  gaussian-p2p-staged: the same exchange driven "
+                         "stage by stage from Python (round-1 path).  gaussian-p2p-allgather: gaussian-p2p followed by an NCCL all-gather of "
+                         "every parameter gradient, so that EVERY rank ends with all gradients (the north-star's literal contract).  "
+                         "replicated: parameters replicated, tile rows sharded, one all-reduce (ShardedGaussianRasterizer)")
     ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--diag", action="store_true", help="per-rank host/all-reduce timing breakdown on stderr")
     ap.add_argument("--cpu-sample-stride", type=int, default=0, help="CPU baseline uses every k-th Gaussian (0 = auto)")
@@ -133,6 +136,20 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str, source: str, workload):
+    """(dram bytes per launch, issue-active %) of `kernel` from profiles/ncu_traffic.json, or (None, None) when the committed capture
+    is for another workload or an older version of the kernel's source file."""
+    import hashlib
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        sha = hashlib.sha256(open(os.path.join(ROOT, "street_gaussians_b200", "csrc", source), "rb").read()).hexdigest()[:16]
+        if workload is not None and j.get("workload") == workload and j.get("source_sha16") == sha:
+            return float(j["dram_bytes"]), j.get("issue_active_pct")
+    except Exception:
+        pass
+    return None, None
+
+
 def make_settings(mod, cam, dev):
     return mod.GaussianRasterizationSettings(
         image_height=cam["image_height"], image_width=cam["image_width"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
@@ -172,6 +189,34 @@ def cpu_baseline(scene, stride: int, budget_pairs: float = 6e8):
                        f"extrapolated x{P / n_sub:.1f} in Gaussian count; R_sample={fw.num_rendered}, pairs={fw.pairs_evaluated}")
     fw.close()
     return info
+
+
+def check_parity_n(mod, rast, scene, cam, dev, rank, world, H, lo, hi, params, means2D, upstream):
+    """Before timing at N > 1: this rank's band of colour / depth / alpha must be BIT-equal to a single-GPU render of the same
+    tensors, and the gradients this rank ends up with — of the Gaussians it owns (Gaussian-sharded) or of all of them (replicated
+    parameters) — within 1e-3 of the single-GPU gradients of the FULL loss (max|d| / max|ref| per tensor, BASELINE.json's bar; the
+    exchange sums the bands, so float summation order is the only expected difference, ~2.5e-5)."""
+    from street_gaussians_b200.sharded import band_of_rows
+    full = {k: scene[k].to(dev).requires_grad_(True) for k in PARAM_KEYS}
+    m2 = torch.zeros((full["means3D"].shape[0], 3), device=dev, requires_grad=True)
+    one = mod.GaussianRasterizer(make_settings(mod, cam, dev))
+    c1, r1, d1, a1, _ = one(means3D=full["means3D"], means2D=m2, opacities=full["opacities"], shs=full["shs"], scales=full["scales"],
+                            rotations=full["rotations"])
+    torch.autograd.backward([c1, d1, a1], [scene[k].to(dev) for k in ("grad_color", "grad_depth", "grad_alpha")])
+    for v in list(params.values()) + [means2D]:
+        v.grad = None
+    color, radii, depth, alpha, _ = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"], shs=params["shs"],
+                                         scales=params["scales"], rotations=params["rotations"])
+    torch.autograd.backward([color, depth, alpha], list(upstream))
+    rows = band_of_rows(H, rank, world).to(dev)
+    ok = all(bool(torch.equal(a.detach()[:, rows], b.detach()[:, rows])) for a, b in ((color, c1), (depth, d1), (alpha, a1)))
+    ok = ok and bool(torch.equal(radii, r1[lo:hi]))
+    worst = 0.0
+    for got, ref in [(params[k].grad, full[k].grad[lo:hi]) for k in PARAM_KEYS] + [(means2D.grad, m2.grad[lo:hi])]:
+        worst = max(worst, float((got.double() - ref.double()).abs().max() / (ref.double().abs().max() + 1e-12)))
+    del full, m2, one, c1, d1, a1
+    torch.cuda.empty_cache()
+    return dict(ok=ok and worst <= 1e-3, grad_rel_max=worst)
 
 
 def main():
@@ -235,8 +280,9 @@ def main():
             from street_gaussians_b200.sharded import GaussianShardedRasterizer
             chunk = (P + world - 1) // world
             rast = GaussianShardedRasterizer(make_settings(mod, cam, dev), capacity=capacity, chunk=chunk,
-                                             exchange="p2p" if args.mp_mode == "gaussian-p2p" else "nccl")
-            if args.mp_mode == "gaussian-p2p":
+                                             exchange="p2p" if args.mp_mode.startswith("gaussian-p2p") else "nccl",
+                                             fused=args.mp_mode != "gaussian-p2p-staged")
+            if args.mp_mode.startswith("gaussian-p2p"):
                 # the peer-memory exchange needs torch symmetric memory (CUDA VMM handles shared between the ranks); if any
                 # rank cannot set it up, ALL ranks fall back to the NCCL exchange (measured 2.5 % slower at N = 8)
                 ok = 1
@@ -254,7 +300,8 @@ def main():
             rast = ShardedGaussianRasterizer(make_settings(mod, cam, dev), capacity=capacity)
 
     gauss_sharded = use_dist and args.mp_mode.startswith("gaussian") and not ref_cuda
-    p2p = gauss_sharded and args.mp_mode == "gaussian-p2p"
+    p2p = gauss_sharded and args.mp_mode.startswith("gaussian-p2p")
+    literal = gauss_sharded and args.mp_mode == "gaussian-p2p-allgather"
     lo, hi = (min(P, rank * chunk), min(P, (rank + 1) * chunk)) if gauss_sharded else (0, P)
     local_scene = {k: scene[k][lo:hi].contiguous() for k in PARAM_KEYS}  # this rank's Gaussians (all of them unless Gaussian-sharded)
     params = {k: local_scene[k].to(dev).requires_grad_(True) for k in PARAM_KEYS}
@@ -272,7 +319,33 @@ def main():
         color, radii, depth, alpha, sem = rast(means3D=p["means3D"], means2D=means2D, opacities=p["opacities"], shs=p["shs"],
                                                scales=p["scales"], rotations=p["rotations"])
         torch.autograd.backward([color, depth, alpha], [gc, gd, ga])
+        if literal:  # north-star literal contract: every rank ends the step holding ALL per-Gaussian gradients
+            for k in PARAM_KEYS:
+                gl = p[k].grad
+                if gl.shape[0] < chunk:
+                    gl = torch.cat([gl, gl.new_zeros((chunk - gl.shape[0],) + tuple(gl.shape[1:]))])
+                dist.all_gather_into_tensor(full_grads[k].view(-1), gl.contiguous().view(-1))
         return color, radii
+
+    full_grads = {k: torch.empty((chunk * world,) + tuple(params[k].shape[1:]), device=dev) for k in PARAM_KEYS} if literal else None
+
+    # ---- N > 1: verify THIS run against a single-GPU render of the same tensors before anything is timed ----
+    parity_n = None
+    if use_dist and not ref_cuda:
+        for _ in range(3):  # exact frame (learns the capacities), first fused frame, steady-state fused frame
+            step()
+        parity_n = check_parity_n(mod, rast, scene, cam, dev, rank, world, H, lo, hi, params, means2D, (gc, gd, ga))
+        ok = torch.tensor([1 if parity_n["ok"] else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        worst = torch.tensor([parity_n["grad_rel_max"]], device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        parity_n = dict(ok=bool(int(ok.item())), images="band rows bit-equal to the single-GPU render on every rank" if int(ok.item()) else "MISMATCH",
+                        grad_rel_max=float(worst.item()), grad_tol=1e-3)
+        if not parity_n["ok"]:
+            if rank == 0:
+                print(json.dumps(dict(error="multi-GPU result differs from the single-GPU render", parity_n=parity_n)))
+            dist.destroy_process_group()
+            return 2
 
     def barrier():
         if use_dist:
@@ -301,6 +374,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.mark(0)
+    launches0 = 0
+    if not ref_cuda:
+        from street_gaussians_b200 import _capi as _sgr_capi
+        launches0 = int(_sgr_capi.lib().sgr_launch_count())
     e0.record()
     for _ in range(args.steps):
         t_h = time.perf_counter()
@@ -309,6 +386,9 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    # kernels of libsgr.so enqueued by THIS rank inside the timed region (counted in the library, cub's sort / scan kernels excluded)
+    gpu_launches = (int(_sgr_capi.lib().sgr_launch_count()) - launches0) if not ref_cuda else 0
+    host_ms = float(np.median(diag["host"]))
     if args.diag:
         ar = [a.elapsed_time(b) for a, b in diag["ar"]]
         print(f"[diag rank {rank}] step {ms_total / args.steps:.3f} ms | host loop per step: median {np.median(diag['host']):.3f} max {max(diag['host']):.3f} ms"
@@ -422,11 +502,11 @@ def main():
         alg_bytes = n_inst * 44 + npx * rows_frac * 28 + visible * 44
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (stages["blend_bwd"] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of blend_bwd2_kernel from the committed `ncu --set full` capture
-        # (profiles/r01_ncu_full.md: 72.97 MB + 3.53 MB); only valid for the workload/size it was captured on
-        traffic = 76.5e6 if (args.workload == "C" and not use_dist) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` capture: only reported when
+        # profiles/ncu_traffic.json holds a capture of THIS workload taken from THIS version of the kernel source (sha256 of the .cu)
+        traffic, issue_pct = ncu_traffic("blend_bwd2_kernel", "blend_bwd2.cu", args.workload if not use_dist else None)
         roofline = dict(bound="hbm", kernel="blend_bwd2_kernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                        traffic=traffic, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
+                        traffic=traffic, issue_active_pct=issue_pct, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
                         note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d; ncu: 76 % issue-active, 1.4 % DRAM): "
                              "real DRAM traffic is 8x BELOW the algorithmic bytes because the tile lists and records are L2 hits; the HBM "
                              "fraction is reported as the contract asks; kernel_ms includes the cudaMemsetAsync of the accumulators")
@@ -507,18 +587,25 @@ def main():
                     config=dict(workload=wl_desc, P=P, visible=visible, width=W, height=H, sh_degree=cam["sh_degree"],
                                 l2="inputs (%.0f MB of Gaussian parameters) exceed the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6),
                                 parallelism=(("Gaussian-sharded x%d (P/N Gaussians + cyclic tile rows per rank): %s; parameters and gradients stay sharded"
-                                              % (world, "48-B records stored / grad2d rows loaded over NVLink peer memory to/from only the ranks whose band "
-                                                        "a Gaussian touches, 2 device-side barriers per step, no NCCL on the data path" if p2p else
+                                              % (world, ("48-B records stored / grad2d rows loaded over NVLink peer memory to/from only the ranks whose band "
+                                                         "a Gaussian touches (stores fused into the projection kernel, loads into the chain-rule kernel), 2 device-side "
+                                                         "barriers per step, no NCCL on the data path" + ("; PLUS an NCCL all-gather of all parameter gradients so every "
+                                                         "rank holds all of them (north-star literal contract)" if literal else "")) if p2p else
                                                  "NCCL all-gather of 48-B records, reduce-scatter of grad2d[P,12]")) if gauss_sharded else
                                              ("tile-row sharded x%d (cyclic rows), parameters replicated, 1 NCCL all-reduce of grad2d[P,12]/step" % world))
                                 if use_dist else "single GPU",
+                                mp_mode=(args.mp_mode if use_dist else None),
                                 num_instances=n_inst, gaussians_pixels_per_s=P * W * H * fps, stage_ms=stages,
+                                stage_ms_note=("per-stage CUDA events of the STAGED calls (one C-ABI call per stage, run after the timed region); "
+                                               "the timed region itself issues each forward / backward as one fused call") if p2p else None,
                                 binning_mode="sync-free (InstanceCapacity)" if args.sync_free else "exact (drop-in default: one 4-byte read-back per forward)",
                                 exact_mode_ms_per_step=exact_ms),
                     e2e=dict(value=1000.0 / e2e_ms, unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                              note="pinned host -> device copy of all 59 floats/Gaussian every step (each rank uploads the Gaussians it owns), double-buffered on a copy stream; scalar loss read back"),
-                    gpu_launches=(((21 if args.sync_free else 20) + (1 if gauss_sharded else 0) + (2 if p2p else 0)) * args.steps) if not ref_cuda else 0,
-                    clocks=clocks)
+                    gpu_launches=gpu_launches, clocks=clocks)
+        line["config"]["host_ms_per_step"] = host_ms
+        if parity_n is not None:
+            line["parity_n"] = parity_n
         if roofline:
             line["roofline"] = roofline
         if cb:

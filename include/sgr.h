@@ -113,10 +113,12 @@ int sgr_forward_bounded(const SgrFrame *frame, const float *means3D, const float
                         const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
                         int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes,
                         void *binning_state, size_t binning_bytes, int64_t capacity, void *stream);
-/* Device->host copy of the status words of the last forward that used geom_state; synchronises `stream`. */
+/* Device->host copy of the status words of the last forward that used geom_state; synchronises `stream`.  `overflowed` is a bit
+ * set: 1 = more instances than `capacity`, 2 = more Gaussians in the band than `gaussian_capacity` (sgr_sharded_forward). */
 int sgr_forward_status(const SgrFrame *frame, const void *geom_state, int64_t *num_instances, int32_t *overflowed, void *stream);
-/* Asynchronous variant: enqueues the copy of two uint32 {instances, overflowed} into host_status (pinned host memory
- * recommended) on `stream` and returns immediately; valid once the caller has observed stream progress past this point. */
+/* Asynchronous variant: enqueues the copy of FOUR uint32 {instances, overflow bits, instances emitted, Gaussians with instances
+ * (compacted mode, else 0)} into host_status (pinned host memory recommended) on `stream` and returns immediately; valid once
+ * the caller has observed stream progress past this point. */
 int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream);
 
 /* Backward, stage 1 of 2: per-pixel backward blend.  Replaces BACKWARD::render
@@ -199,11 +201,47 @@ typedef struct SgrPeers {
 	void *records[SGR_MAX_PEERS];       /* rank p's gathered record array (= start of its geom_state), world*chunk records */
 	int32_t *radii[SGR_MAX_PEERS];      /* rank p's radii[world*chunk] */
 	const float *grad2d[SGR_MAX_PEERS]; /* rank p's partial grad2d[world*chunk,12] (output of its sgr_backward_blend) */
+	uint32_t *flags[SGR_MAX_PEERS];     /* rank p's barrier pad: uint32[SGR_MAX_PEERS], zero-initialised once by the caller and mapped
+	                                       into every rank like the arrays above.  Only needed by sgr_peer_barrier / sgr_sharded_*. */
 } SgrPeers;
 int sgr_scatter_records(const SgrFrame *frame, const SgrPeers *peers, const void *records_local, const int32_t *radii_local,
                         void *stream);
 int sgr_gather_grad2d(const SgrFrame *frame, const SgrPeers *peers, const void *records_local, const int32_t *radii_local,
                       float *grad2d_local, void *stream);
+
+/* Device-side barrier across the ranks of `peers` on `stream` (no host involvement, no NCCL): each rank stores `epoch` into its
+ * slot of every peer's pad (release, system scope, after fencing its earlier peer stores) and waits until every peer has stored
+ * an epoch >= `epoch` into its own pad.  Every rank must issue the same sequence of barriers with epochs increasing by one
+ * (first epoch 1).  The wait is bounded (2 s): a rank that never arrives cannot wedge the GPU. */
+int sgr_peer_barrier(const SgrPeers *peers, uint32_t epoch, void *stream);
+
+/* The Gaussian-sharded forward as ONE call (steps 1-3 above with the peer-memory exchange): project the rank's frame.P Gaussians and
+ * store every record straight into the gathered arrays of the ranks whose band it meets (one kernel), device barrier, then bin /
+ * sort / blend the rank's band from its gathered records — ~28 kernel launches issued back to back from C instead of six
+ * Python-level calls (the N = 8 step was host-launch bound: profiles/r01_bench_n8_gaussian_p2p_diag.txt).
+ *   frame.P = local Gaussian count; frame.row_* = this rank's CYCLIC band (row_begin == rank, row_step == world); S must be 0.
+ *   peers->records[rank] is this rank's geom_state (sgr_state_sizes for P = world*chunk, `geom_bytes` bytes) whose first
+ *   world*chunk records are the gather target; radii_local[chunk] / records_local[chunk] receive the rank's own results (kept
+ *   for sgr_sharded_backward).  Bounded mode only: `capacity` instances (binning_state of sgr_binning_bytes(capacity)) and
+ *   `gaussian_capacity` depth-order slots (< 0: sort all world*chunk Gaussians; otherwise only the Gaussians with instances in
+ *   this band are compacted and sorted — sgr_forward_status reports both counts and both overflow bits).
+ *   barrier_epoch: epoch of the barrier after the scatter; with pre_barrier != 0 a barrier with epoch barrier_epoch - 1 is issued
+ *   first (needed when the previous call on this workspace was a forward without a backward: peers may still be reading the
+ *   records this call overwrites).  The rows of peers->grad2d[rank] that a backward can touch are zeroed by this call. */
+int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const float *means3D, const float *shs, const float *colors_precomp,
+                        const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp, float *out_color,
+                        float *out_depth, float *out_alpha, int32_t *radii_local, void *records_local, size_t geom_bytes, void *img_state,
+                        size_t img_bytes, void *binning_state, size_t binning_bytes, int64_t capacity, int64_t gaussian_capacity,
+                        uint32_t barrier_epoch, int32_t pre_barrier, void *stream);
+/* The matching backward as ONE call (steps 4-5): blend_bwd of the band into peers->grad2d[rank], device barrier (barrier_epoch), then
+ * the per-Gaussian chain rule of the rank's frame.P Gaussians, which sums each Gaussian's 12 screen-space values from the
+ * ranks that rendered it while it runs (no separate gather pass, no reduce-scatter).  Outputs as in sgr_backward_geom. */
+int sgr_sharded_backward(const SgrFrame *frame, const SgrPeers *peers, int64_t capacity, const float *means3D, const float *shs,
+                         const float *colors_precomp, const float *scales, const float *rotations, const float *cov3D_precomp,
+                         const int32_t *radii_local, const void *records_local, const void *img_state, const void *binning_state,
+                         const float *out_alpha, const float *dL_dcolor, const float *dL_ddepth, const float *dL_dalpha,
+                         float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
+                         float *dL_dscales, float *dL_drotations, float *dL_dcov3D, uint32_t barrier_epoch, void *stream);
 
 /* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
  * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */

@@ -14,7 +14,7 @@ SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_launch_count", "sgr_state_s
            "sgr_forward_status", "sgr_forward_status_async", "sgr_backward_blend",
            "sgr_backward_geom", "sgr_backward", "sgr_mark_visible", "sgr_visible_filter", "sgr_knn_scratch_bytes",
            "sgr_knn_mean_dist2", "sgr_record_bytes", "sgr_project", "sgr_forward_records",
-           "sgr_scatter_records", "sgr_gather_grad2d"]
+           "sgr_scatter_records", "sgr_gather_grad2d", "sgr_peer_barrier", "sgr_sharded_forward", "sgr_sharded_backward"]
 
 
 class SgrFrame(C.Structure):
@@ -29,7 +29,7 @@ MAX_PEERS = 16
 
 class SgrPeers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("chunk", C.c_int64), ("records", C.c_void_p * MAX_PEERS),
-                ("radii", C.c_void_p * MAX_PEERS), ("grad2d", C.c_void_p * MAX_PEERS)]
+                ("radii", C.c_void_p * MAX_PEERS), ("grad2d", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS)]
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -85,6 +85,14 @@ def lib():
     L.sgr_scatter_records.argtypes = [C.POINTER(SgrFrame), C.POINTER(SgrPeers), vp, vp, vp]
     L.sgr_gather_grad2d.restype = C.c_int
     L.sgr_gather_grad2d.argtypes = [C.POINTER(SgrFrame), C.POINTER(SgrPeers), vp, vp, vp, vp]
+    L.sgr_peer_barrier.restype = C.c_int
+    L.sgr_peer_barrier.argtypes = [C.POINTER(SgrPeers), C.c_uint32, vp]
+    L.sgr_sharded_forward.restype = C.c_int
+    L.sgr_sharded_forward.argtypes = [C.POINTER(SgrFrame), C.POINTER(SgrPeers)] + [vp] * 7 + [vp] * 3 + [vp, vp, C.c_size_t, vp, C.c_size_t, vp,
+                                                                                                C.c_size_t, C.c_int64, C.c_int64, C.c_uint32,
+                                                                                                C.c_int32, vp]
+    L.sgr_sharded_backward.restype = C.c_int
+    L.sgr_sharded_backward.argtypes = [C.POINTER(SgrFrame), C.POINTER(SgrPeers), C.c_int64] + [vp] * 6 + [vp] * 4 + [vp] * 4 + [vp] * 8 + [C.c_uint32, vp]
     L.sgr_backward_blend.restype = C.c_int
     L.sgr_backward_blend.argtypes = [C.POINTER(SgrFrame), C.c_int64] + [vp] * 12
     L.sgr_backward_geom.restype = C.c_int

@@ -12,6 +12,7 @@
 // exact cull (tile_visit.cuh); tests/test_parity_gpu.py checks images bit-for-bit / to 1e-6 against the reference.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -21,18 +22,29 @@
 namespace sgr {
 
 struct GatherCount {
-	const uint32_t *tiles_touched, *perm;
-	__host__ __device__ __forceinline__ uint32_t operator()(int t) const { return tiles_touched[perm[t]]; }
+	const uint32_t *tiles_touched, *perm, *depth_sorted;
+	// entries whose sorted key is 0xFFFFFFFF emit nothing: Gaussians without instances (uncompacted order) or the padding
+	// behind the selected ones (compacted order, where perm is meaningless) — a real view depth > 0.2 never has those bits
+	__host__ __device__ __forceinline__ uint32_t operator()(int t) const {
+		return depth_sorted[t] == 0xffffffffu ? 0u : tiles_touched[perm[t]];
+	}
+};
+struct HasInstances {
+	const uint32_t *tiles_touched;
+	__host__ __device__ __forceinline__ bool operator()(int i) const { return tiles_touched[i] > 0u; }
 };
 using CountIter = cub::TransformInputIterator<uint32_t, GatherCount, cub::CountingInputIterator<int>>;
 
 size_t geom_temp_bytes(int P) {
 	const int n = P > 0 ? P : 1;
 	size_t a = 0, b = 0;
-	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{nullptr, nullptr});
+	size_t c = 0;
+	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{nullptr, nullptr, nullptr});
 	cub::DeviceScan::InclusiveSum(nullptr, a, it, (uint32_t *)nullptr, n);
 	cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, n);
-	return a > b ? a : b;
+	cub::DeviceSelect::If(nullptr, c, cub::CountingInputIterator<int>(0), (uint32_t *)nullptr, (uint32_t *)nullptr, n, HasInstances{nullptr});
+	a = a > b ? a : b;
+	return a > c ? a : c;
 }
 size_t sort_temp_bytes(int64_t R) {
 	size_t a = 0, b = 0;
@@ -46,9 +58,13 @@ size_t sort_temp_bytes(int64_t R) {
 // the tail of preprocess_fwd_kernel — instance count against THIS rank's tile-row band, depth sort key, identity
 // permutation — runs here from the 48-B record + radius.  Same tile_rect / make_cull / visit_tiles as the emission
 // kernels below, so counts and emitted ranges agree by construction.
+// zero_rows (nullable): this rank's partial grad2d[P,12].  The rows of the Gaussians delivered to this rank (radius != 0 <=>
+// rectangle meets the band) are the only ones its blend_bwd can touch and the only ones their owners read back, so they are
+// zeroed here — 48 B x (Gaussians in the band) instead of a 48 B x P_total memset in front of every backward.
 __global__ void __launch_bounds__(256) count_tiles_kernel(const FrameDev f, const GaussRec *__restrict__ rec,
                                                          const int32_t *__restrict__ radii, uint32_t *__restrict__ tiles_touched,
-                                                         uint32_t *__restrict__ depth_key, uint32_t *__restrict__ iota) {
+                                                         uint32_t *__restrict__ depth_key, uint32_t *__restrict__ iota,
+                                                         float4 *__restrict__ zero_rows) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = idx < f.P;
 	bool ok = false;
@@ -63,6 +79,10 @@ __global__ void __launch_bounds__(256) count_tiles_kernel(const FrameDev f, cons
 			cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
 			depth = q1.w;
 			ok = true;
+			if (zero_rows) {
+				const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+				zero_rows[3 * (size_t)idx] = z; zero_rows[3 * (size_t)idx + 1] = z; zero_rows[3 * (size_t)idx + 2] = z;
+			}
 		}
 	}
 	uint32_t count = 0;
@@ -73,22 +93,60 @@ __global__ void __launch_bounds__(256) count_tiles_kernel(const FrameDev f, cons
 		iota[idx] = (uint32_t)idx;
 	}
 }
-cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st) {
+cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st, float *zero_rows) {
 	if (f.P == 0) return cudaSuccess;
 	count_launch();
-	count_tiles_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.depth_key, g.iota);
+	count_tiles_kernel<<<(f.P + 255) / 256, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.depth_key, g.iota,
+	                                                      reinterpret_cast<float4 *>(zero_rows));
 	return cudaGetLastError();
 }
 
-// depth order of the Gaussians + inclusive scan of their instance counts in that order
-cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st) {
+// Compacted mode, step 2: keys / values of the depth sort for the first `cap_v` selected Gaussians, 0xFFFFFFFF padding behind
+// them; raises the Gaussian-capacity overflow bit when more were selected than fit.
+__global__ void __launch_bounds__(256) compact_keys_kernel(const uint32_t *__restrict__ sel, const uint32_t *__restrict__ depth_key,
+                                                          uint32_t *__restrict__ ckey, uint32_t *__restrict__ cval, uint32_t cap_v,
+                                                          uint32_t *__restrict__ status) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n_sel = status[4];
+	if (j == 0 && n_sel > cap_v) atomicOr(&status[2], 2u);
+	if (j >= cap_v) return;
+	const bool live = j < n_sel;
+	const uint32_t g = live ? sel[j] : 0u;
+	ckey[j] = live ? depth_key[g] : 0xffffffffu;
+	cval[j] = g;
+}
+
+// depth order of the Gaussians + inclusive scan of their instance counts in that order.
+//   cap_v < 0 : all f.P Gaussians take part (those without instances carry the key 0xFFFFFFFF and sort to the end);
+//   cap_v >= 0: only the Gaussians WITH instances in this rank's band are sorted (ordered stream compaction, then a sort of
+//               `cap_v` slots).  With N tile-row bands a rank sees ~1/N .. 2/N of the visible Gaussians, and the 4-pass sort over
+//               all P was the largest replicated stage of the Gaussian-sharded forward (profiles/r01_summary.md §5).
+// Returns the number of depth-order slots (f.P or cap_v) through *n_order: the emit kernels run over that many.
+cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st, int64_t cap_v, int *n_order) {
+	if (n_order) *n_order = f.P;
 	if (f.P == 0) return cudaSuccess;
 	size_t bytes = g.temp_bytes;
-	cudaError_t e = cub::DeviceRadixSort::SortPairs(g.temp, bytes, g.depth_key, g.depth_sorted, g.iota, g.perm, f.P, 0, 32, st);
+	cudaError_t e;
+	int n = f.P;
+	if (cap_v >= 0) {
+		n = (int)(cap_v < (int64_t)f.P ? cap_v : (int64_t)f.P);
+		if (n < 1) n = 1;
+		// ascending indices of the Gaussians with instances -> g.iota[0 .. n_sel), n_sel -> status word 4 (stable: index order kept)
+		e = cub::DeviceSelect::If(g.temp, bytes, cub::CountingInputIterator<int>(0), g.iota, g.big_count + 4, f.P, HasInstances{g.tiles_touched}, st);
+		if (e != cudaSuccess) return e;
+		count_launch();
+		compact_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g.iota, g.depth_key, g.ckey, g.cval, (uint32_t)n, g.big_count);
+		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+		bytes = g.temp_bytes;
+		e = cub::DeviceRadixSort::SortPairs(g.temp, bytes, g.ckey, g.depth_sorted, g.cval, g.perm, n, 0, 32, st);
+	} else {
+		e = cub::DeviceRadixSort::SortPairs(g.temp, bytes, g.depth_key, g.depth_sorted, g.iota, g.perm, n, 0, 32, st);
+	}
 	if (e != cudaSuccess) return e;
-	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{g.tiles_touched, g.perm});
+	if (n_order) *n_order = n;
+	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{g.tiles_touched, g.perm, g.depth_sorted});
 	bytes = g.temp_bytes;
-	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, f.P, st);
+	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, n, st);
 }
 
 constexpr uint32_t kEmitStage = 512;  // instances staged per warp (2 x 2 KB of shared memory per warp)
@@ -100,7 +158,7 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
                                                         const uint32_t *__restrict__ /*tiles_touched*/, const uint32_t *__restrict__ perm,
                                                         const uint32_t *__restrict__ offsets, KeyT *__restrict__ keys,
                                                         uint32_t *__restrict__ vals, uint32_t *__restrict__ big_list,
-                                                        uint32_t *__restrict__ big_count, const uint32_t cap) {
+                                                        uint32_t *__restrict__ big_count, const uint32_t cap, const int n_order) {
 	__shared__ KeyT s_keys[8][kEmitStage];
 	__shared__ uint32_t s_vals[8][kEmitStage];
 	const int warp = threadIdx.x >> 5;
@@ -110,10 +168,10 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 	CullParams cp = {};
 	uint32_t gidx = 0;
 	// [off, end) = this Gaussian's output range (offsets = inclusive scan in depth order); lanes past P get an empty range
-	const int tc = min(t, f.P - 1);
+	const int tc = min(t, n_order - 1);  // n_order = depth-order slots: f.P, or the Gaussian capacity of the compacted mode
 	uint32_t end = offsets[tc];
 	uint32_t off = tc == 0 ? 0u : offsets[tc - 1];
-	if (t >= f.P) off = end;
+	if (t >= n_order) off = end;
 	// bounded mode: a Gaussian whose range does not fit the caller's capacity emits nothing.  BOTH ends are clamped so that
 	// warp_first / warp_last (taken from lanes 0 / 31 below) never address past `cap`, even when every lane of the warp
 	// overflows: the staged flush then covers at most [warp_first, cap), and pad_keys_kernel rewrites [emitted, cap).
@@ -121,9 +179,9 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(const FrameDev f, const
 		off = min(off, cap);
 		end = off;
 	}
-	if (t < f.P) {
-		gidx = perm[t];
+	if (t < n_order) {
 		if (end > off) {
+			gidx = perm[t];  // (padding slots of the compacted order have end == off and a meaningless perm)
 			const float4 q0 = rec[gidx].q0, q1 = rec[gidx].q1;
 			tile_rect(q0.x, q0.y, radii[gidx], f.gx, f.gy, x0, y0, x1, y1);
 			cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
@@ -214,7 +272,7 @@ __global__ void count_status_kernel(const uint32_t *__restrict__ offsets, int P,
 		emitted = lo == 0 ? 0u : offsets[lo - 1];
 	}
 	status[1] = R;
-	status[2] = R > cap ? 1u : 0u;
+	status[2] |= R > cap ? 1u : 0u;  // (bit 1 = Gaussian-capacity overflow of the compacted depth order; the words are zeroed per forward)
 	status[3] = emitted;
 }
 template <typename KeyT>
@@ -234,7 +292,8 @@ static int bits_for(uint32_t n) {  // smallest b with (1 << b) >= n, i.e. enough
 }
 
 cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, BinView b, ImgView img, int64_t R, cudaStream_t st,
-                           int64_t cap) {
+                           int64_t cap, int n_order) {
+	if (n_order < 0) n_order = f.P;
 	const int ntile = f.gx * f.gy;
 	const bool bounded = cap >= 0;
 	cudaError_t e = cudaMemsetAsync(img.ranges, 0, (size_t)ntile * sizeof(uint2), st);
@@ -242,12 +301,12 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 	if (f.P == 0) return cudaSuccess;
 	const uint32_t cap32 = bounded ? (uint32_t)cap : 0xffffffffu;
 	count_launch();
-	count_status_kernel<<<1, 1, 0, st>>>(g.offsets, f.P, cap32, g.big_count);
+	count_status_kernel<<<1, 1, 0, st>>>(g.offsets, n_order, cap32, g.big_count);
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if (bounded) R = cap;  // every pass below runs over the caller's capacity; the padding carries the largest key
 	if (R == 0) return cudaSuccess;
 	size_t bytes = b.sort_temp_bytes;
-	const unsigned nblk = (unsigned)((f.P + 255) / 256);
+	const unsigned nblk = (unsigned)((n_order + 255) / 256);
 	const unsigned nbig_blk = 148 * 4;  // persistent-style grid for the deferred large rectangles
 	if ((e = cudaMemsetAsync(g.big_count, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
 	const unsigned npad_blk = bounded ? (unsigned)((cap + 255) / 256) : 0u;  // upper bound; threads past `cap` exit
@@ -255,7 +314,7 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 	if (ntile <= 65535 || (!bounded && ntile <= 65536)) {  // 16-bit tile ids (the key arrays are allocated for 32-bit ids either way)
 		uint16_t *kin = reinterpret_cast<uint16_t *>(b.keys_in), *kout = reinterpret_cast<uint16_t *>(b.keys_out);
 		count_launch();
-		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32);
+		emit_pairs_kernel<uint16_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32, n_order);
 		count_launch();
 		emit_big_kernel<uint16_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, kin, b.vals_in, g.big_list, g.big_count, cap32);
 		if (bounded) count_launch();
@@ -267,7 +326,7 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 		tile_ranges_kernel<uint16_t><<<(unsigned)((R + 256 * kRangeKeysPerThread - 1) / (256 * kRangeKeysPerThread)), 256, 0, st>>>(R, kout, img.ranges, (uint32_t)ntile);
 	} else {
 		count_launch();
-		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
+		emit_pairs_kernel<uint32_t><<<nblk, 256, 0, st>>>(f, g.rec, radii, g.tiles_touched, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32, n_order);
 		count_launch();
 		emit_big_kernel<uint32_t><<<nbig_blk, 256, 0, st>>>(f, g.rec, radii, g.perm, g.offsets, b.keys_in, b.vals_in, g.big_list, g.big_count, cap32);
 		if (bounded) count_launch();

@@ -246,9 +246,9 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 }
 
 cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *out_alpha, const float *dL_dcolor,
-                              const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st) {
+                              const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st, bool grad2d_zeroed) {
 	if (f.P == 0) return cudaSuccess;
-	cudaError_t e = cudaMemsetAsync(grad2d, 0, (size_t)f.P * 12 * sizeof(float), st);
+	cudaError_t e = grad2d_zeroed ? cudaSuccess : cudaMemsetAsync(grad2d, 0, (size_t)f.P * 12 * sizeof(float), st);
 	if (e != cudaSuccess) return e;
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;

@@ -54,6 +54,8 @@ GeomView carve_geom(void *base, int P) {
 	g.offsets = take<uint32_t>(p, n);
 	g.big_list = take<uint32_t>(p, n);
 	g.big_count = take<uint32_t>(p, 64);
+	g.ckey = take<uint32_t>(p, n);
+	g.cval = take<uint32_t>(p, n);
 	g.temp_bytes = memo_bytes((int64_t)P, [](int64_t n) { return geom_temp_bytes((int)n); });
 	g.temp = take<char>(p, g.temp_bytes);
 	g.total_bytes = (size_t)(p - reinterpret_cast<char *>(base));
@@ -181,7 +183,7 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
                         const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
                         int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
                         void *alloc_user, void **binning_state, int64_t *num_instances, void *bounded_state, size_t bounded_bytes,
-                        int64_t capacity, void *stream, bool from_records = false) {
+                        int64_t capacity, void *stream, bool from_records = false, int64_t gaussian_capacity = -1) {
 	FrameDev f;
 	int rc = make_frame(frame, f);
 	if (rc) return rc;
@@ -216,16 +218,18 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
 	}
 
 	int64_t R = 0;
+	int n_order = f.P;
 	BinView b = carve_bin(nullptr, 0);
 	if (f.P > 0) {
+		SGR_TRY(cudaMemsetAsync(g.big_count, 0, 64 * sizeof(uint32_t), st), "status reset");
 		if (from_records) SGR_TRY(launch_count_tiles(f, g, radii, st), "count_tiles");
 		else
 			SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
 			        "preprocess_fwd");
-		SGR_TRY(launch_depth_order(f, g, st), "depth_order");
+		SGR_TRY(launch_depth_order(f, g, st, bounded ? gaussian_capacity : -1, &n_order), "depth_order");
 		if (!bounded) {
 			uint32_t r32 = 0;
-			cudaError_t e = read_back_u32(&r32, g.offsets + (f.P - 1), st);
+			cudaError_t e = read_back_u32(&r32, g.offsets + (n_order - 1), st);
 			if (e != cudaSuccess) return fail(SGR_ECUDA, "instance count read-back: %s", cudaGetErrorString(e));
 			R = (int64_t)r32;
 			if (R > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "instance count %lld exceeds 2^31-1", (long long)R);
@@ -243,7 +247,7 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
 		if (binning_state) *binning_state = bin;
 	}
 	if (num_instances) *num_instances = R;
-	SGR_TRY(launch_binning(f, g, radii, b, img, R, st, bounded ? capacity : -1), "binning");
+	SGR_TRY(launch_binning(f, g, radii, b, img, R, st, bounded ? capacity : -1, n_order), "binning");
 	SGR_TRY(launch_blend_fwd(f, g, b, img, semantics, out_color, out_depth, out_alpha, out_semantic, st), "blend_fwd");
 	return SGR_OK;
 }
@@ -314,6 +318,7 @@ static int make_peers(const SgrPeers *peers, const FrameDev &f, bool need_grad, 
 		pt.rec[p] = reinterpret_cast<GaussRec *>(peers->records[p]);
 		pt.radii[p] = peers->radii[p];
 		pt.grad2d[p] = peers->grad2d[p];
+		pt.flags[p] = peers->flags[p];
 	}
 	return SGR_OK;
 }
@@ -346,21 +351,135 @@ int sgr_gather_grad2d(const SgrFrame *frame, const SgrPeers *peers, const void *
 	return SGR_OK;
 }
 
+int sgr_peer_barrier(const SgrPeers *peers, uint32_t epoch, void *stream) {
+	if (!peers) return fail(SGR_EINVAL, "peers is NULL");
+	FrameDev f = {};
+	PeerTable pt = {};
+	int rc = make_peers(peers, f, false, pt);
+	if (rc) return rc;
+	for (int p = 0; p < pt.world; p++)
+		if (!pt.flags[p]) return fail(SGR_EINVAL, "peer table entry %d has no barrier pad", p);
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_peer_barrier(pt, epoch, nullptr, st), "peer_barrier");
+	return SGR_OK;
+}
+
+// FrameDev of the gathered problem (all world*chunk slots) seen through this rank's band
+static int make_total_frame(const SgrFrame *frame, const SgrPeers *peers, FrameDev &fl, FrameDev &ft, PeerTable &pt, bool need_grad) {
+	int rc = make_frame(frame, fl);
+	if (rc) return rc;
+	if ((rc = make_peers(peers, fl, need_grad, pt)) != SGR_OK) return rc;
+	if (fl.S != 0) return fail(SGR_EUNSUPPORTED, "the fused Gaussian-sharded step supports S == 0 only (use the staged calls for feature channels)");
+	for (int p = 0; p < pt.world; p++)
+		if (pt.world > 1 && !pt.flags[p]) return fail(SGR_EINVAL, "peer table entry %d has no barrier pad", p);
+	if (pt.world > 1 && !(fl.band.step == pt.world && fl.band.begin == pt.rank))
+		return fail(SGR_EINVAL, "the peer exchange needs the cyclic band of this rank: begin == rank, step == world (got [%d,%d) step %d)",
+		            fl.band.begin, fl.band.end, fl.band.step);
+	ft = fl;
+	ft.P = (int)(pt.chunk * pt.world);
+	return SGR_OK;
+}
+
+int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const float *means3D, const float *shs, const float *colors_precomp,
+                        const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp, float *out_color,
+                        float *out_depth, float *out_alpha, int32_t *radii_local, void *records_local, size_t geom_bytes, void *img_state,
+                        size_t img_bytes, void *binning_state, size_t binning_bytes, int64_t capacity, int64_t gaussian_capacity,
+                        uint32_t barrier_epoch, int32_t pre_barrier, void *stream) {
+	FrameDev fl, ft;
+	PeerTable pt = {};
+	int rc = make_total_frame(frame, peers, fl, ft, pt, false);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (capacity < 0 || capacity > 0x7fffffffLL) return fail(SGR_EINVAL, "capacity must be in [0, 2^31)");
+	if (!out_color || !out_depth || !out_alpha) return fail(SGR_EINVAL, "output image pointer is NULL");
+	if (!fl.bg || !fl.view || !fl.proj || !fl.campos) return fail(SGR_EINVAL, "camera pointer (bg/viewmatrix/projmatrix/campos) is NULL");
+	if (pt.chunk > 0 && (!radii_local || !records_local)) return fail(SGR_EINVAL, "radii_local / records_local is NULL");
+	if (fl.P > 0) {
+		if (!means3D || !opacities) return fail(SGR_EINVAL, "means3D / opacities is NULL");
+		if ((shs == nullptr) == (colors_precomp == nullptr)) return fail(SGR_EINVAL, "provide exactly one of shs / colors_precomp");
+		const bool sr = scales != nullptr && rotations != nullptr;
+		if (sr == (cov3D_precomp != nullptr) || ((scales != nullptr) != (rotations != nullptr)))
+			return fail(SGR_EINVAL, "provide exactly one of (scales, rotations) / cov3D_precomp");
+		if (shs && fl.M <= 0) return fail(SGR_EINVAL, "shs given but M == 0");
+	}
+	void *geom_state = pt.rec[pt.rank];  // this rank's gathered records ARE the head of its geom state
+	const GeomView g = carve_geom(geom_state, ft.P);
+	const ImgView img = carve_img(img_state, ft.W, ft.H);
+	if (geom_bytes < g.total_bytes) return fail(SGR_ENOMEM, "geom_state too small: %zu < %zu", geom_bytes, g.total_bytes);
+	if (!img_state || img_bytes < img.total_bytes) return fail(SGR_ENOMEM, "img_state too small: %zu < %zu", img_bytes, img.total_bytes);
+	const size_t need = carve_bin(nullptr, capacity).total_bytes;
+	if (capacity > 0 && (!binning_state || binning_bytes < need))
+		return fail(SGR_ENOMEM, "binning_state too small for capacity %lld: %zu < %zu", (long long)capacity, binning_bytes, need);
+	// a forward that follows a forward (no backward in between) must not overwrite records a peer may still be blending
+	if (pre_barrier) SGR_TRY(launch_peer_barrier(pt, barrier_epoch - 1u, nullptr, st), "pre-barrier");
+	SGR_TRY(launch_project_scatter(fl, pt, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii_local,
+	                               reinterpret_cast<GaussRec *>(records_local), st),
+	        "project+scatter");
+	if (ft.P == 0) return SGR_OK;
+	SGR_TRY(cudaMemsetAsync(g.big_count, 0, 64 * sizeof(uint32_t), st), "status reset");
+	SGR_TRY(launch_peer_barrier(pt, barrier_epoch, g.big_count, st), "barrier");
+	int n_order = ft.P;
+	SGR_TRY(launch_count_tiles(ft, g, pt.radii[pt.rank], st, const_cast<float *>(pt.grad2d[pt.rank])), "count_tiles");
+	SGR_TRY(launch_depth_order(ft, g, st, gaussian_capacity, &n_order), "depth_order");
+	const BinView b = capacity > 0 ? carve_bin(binning_state, capacity) : carve_bin(nullptr, 0);
+	SGR_TRY(launch_binning(ft, g, pt.radii[pt.rank], b, img, capacity, st, capacity, n_order), "binning");
+	SGR_TRY(launch_blend_fwd(ft, g, b, img, nullptr, out_color, out_depth, out_alpha, nullptr, st), "blend_fwd");
+	return SGR_OK;
+}
+
+int sgr_sharded_backward(const SgrFrame *frame, const SgrPeers *peers, int64_t capacity, const float *means3D, const float *shs,
+                         const float *colors_precomp, const float *scales, const float *rotations, const float *cov3D_precomp,
+                         const int32_t *radii_local, const void *records_local, const void *img_state, const void *binning_state,
+                         const float *out_alpha, const float *dL_dcolor, const float *dL_ddepth, const float *dL_dalpha,
+                         float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
+                         float *dL_dscales, float *dL_drotations, float *dL_dcov3D, uint32_t barrier_epoch, void *stream) {
+	FrameDev fl, ft;
+	PeerTable pt = {};
+	int rc = make_total_frame(frame, peers, fl, ft, pt, true);
+	if (rc) return rc;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = frame->debug != 0;
+	if (!img_state || !out_alpha || !dL_dcolor || !dL_ddepth || !dL_dalpha) return fail(SGR_EINVAL, "NULL pointer passed to sgr_sharded_backward");
+	if (capacity > 0 && !binning_state) return fail(SGR_EINVAL, "capacity > 0 but binning_state is NULL");
+	if (fl.P > 0) {
+		if (!means3D || !radii_local || !records_local || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity)
+			return fail(SGR_EINVAL, "NULL pointer passed to sgr_sharded_backward");
+		if (shs && !dL_dsh) return fail(SGR_EINVAL, "shs given but dL_dsh is NULL");
+		if (!cov3D_precomp && (!scales || !rotations || !dL_dscales || !dL_drotations))
+			return fail(SGR_EINVAL, "scale/rotation path needs scales, rotations, dL_dscales, dL_drotations");
+	}
+	const GeomView g = carve_geom(pt.rec[pt.rank], ft.P);
+	const ImgView img = carve_img(const_cast<void *>(img_state), ft.W, ft.H);
+	const BinView b = carve_bin(const_cast<void *>(binning_state), capacity);
+	float *grad2d = const_cast<float *>(pt.grad2d[pt.rank]);
+	if (ft.P > 0)
+		SGR_TRY(launch_blend_bwd(ft, g, b, img, nullptr, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, nullptr, grad2d, nullptr, st, true), "blend_bwd");
+	SGR_TRY(launch_peer_barrier(pt, barrier_epoch, ft.P > 0 ? g.big_count : nullptr, st), "barrier");
+	SGR_TRY(launch_preprocess_bwd_gather(fl, pt, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii_local,
+	                                     reinterpret_cast<const GaussRec *>(records_local), dL_dmeans3D, dL_dmeans2D, shs ? dL_dsh : nullptr,
+	                                     dL_dcolors_precomp, dL_dopacity, cov3D_precomp ? nullptr : dL_dscales,
+	                                     cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, st),
+	        "preprocess_bwd+gather");
+	return SGR_OK;
+}
+
 int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream) {
 	FrameDev f;
 	int rc = make_frame(frame, f);
 	if (rc) return rc;
 	if (!geom_state || !host_status) return fail(SGR_EINVAL, "NULL pointer passed to sgr_forward_status_async");
-	host_status[0] = host_status[1] = 0;
+	host_status[0] = host_status[1] = host_status[2] = host_status[3] = 0;
 	if (f.P == 0) return SGR_OK;
 	const GeomView g = carve_geom(const_cast<void *>(geom_state), f.P);
-	cudaError_t e = cudaMemcpyAsync(host_status, g.big_count + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream));
+	cudaError_t e = cudaMemcpyAsync(host_status, g.big_count + 1, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream));
 	if (e != cudaSuccess) return fail(SGR_ECUDA, "status copy: %s", cudaGetErrorString(e));
 	return SGR_OK;
 }
 
 int sgr_forward_status(const SgrFrame *frame, const void *geom_state, int64_t *num_instances, int32_t *overflowed, void *stream) {
-	uint32_t h[2] = {0, 0};
+	uint32_t h[4] = {0, 0, 0, 0};
 	int rc = sgr_forward_status_async(frame, geom_state, h, stream);
 	if (rc) return rc;
 	cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));

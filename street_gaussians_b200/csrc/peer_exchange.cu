@@ -11,15 +11,6 @@
 
 namespace sgr {
 
-// ranks whose cyclic band meets tile rows [y0, y1)
-__device__ __forceinline__ uint32_t touched_ranks(int y0, int y1, int world) {
-	if (y1 <= y0) return 0u;
-	if (y1 - y0 >= world) return world >= 32 ? 0xffffffffu : ((1u << world) - 1u);
-	uint32_t m = 0u;
-	for (int y = y0; y < y1; y++) m |= 1u << (y % world);
-	return m;
-}
-
 __device__ __forceinline__ uint32_t ranks_of(const FrameDev &f, const float4 q0, int radius, int world) {
 	int x0, y0, x1, y1;
 	tile_rect(q0.x, q0.y, radius, f.gx, f.gy, x0, y0, x1, y1);
@@ -71,6 +62,41 @@ __global__ void __launch_bounds__(256) gather_grad2d_kernel(const FrameDev f, co
 	}
 	float4 *dst = reinterpret_cast<float4 *>(out + (size_t)idx * 12);
 	dst[0] = a; dst[1] = b; dst[2] = c;
+}
+
+// Cross-rank barrier on the caller's stream: thread p announces this rank's arrival in rank p's pad (a release store at system
+// scope, after a system-scope fence that orders this rank's earlier peer stores — issued by previous kernels of the stream —
+// before it) and then waits until rank p has announced itself in this rank's pad.  Epochs increase by one per barrier and every
+// rank issues the same sequence of barriers, so one pad suffices: a peer that is already one barrier ahead has written a larger
+// epoch, which also satisfies the wait.  The spin is bounded (2 s) so a missing peer cannot wedge the GPU; a timeout sets
+// status[5] and the frame is garbage.
+__global__ void peer_barrier_kernel(const PeerTable pt, const uint32_t epoch, uint32_t *__restrict__ status) {
+	const int p = threadIdx.x;
+	if (p >= pt.world) return;
+	__threadfence_system();
+	uint32_t *theirs = pt.flags[p] + pt.rank;
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+	const uint32_t *mine = pt.flags[pt.rank] + p;
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for (;;) {
+		uint32_t v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+		if ((int32_t)(v - epoch) >= 0) break;
+		__nanosleep(40);
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > 2000000000ull) {
+			if (status) atomicExch(&status[5], epoch);
+			break;
+		}
+	}
+}
+cudaError_t launch_peer_barrier(const PeerTable &pt, uint32_t epoch, uint32_t *status, cudaStream_t st) {
+	if (pt.world <= 1) return cudaSuccess;
+	count_launch();
+	peer_barrier_kernel<<<1, 32, 0, st>>>(pt, epoch, status);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_scatter_records(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, cudaStream_t st) {

@@ -35,9 +35,12 @@ __device__ __forceinline__ M3 rot_colmajor(const float4 q) {
 
 constexpr int kShRow = 49;  // padded smem row (floats) for up to 16 x 3 SH coefficients
 
-template <bool STAGED>
+// GATHER = true (sgr_sharded_backward): grad2d is not a local array — the 12 sums of local Gaussian idx (global id
+// rank*chunk + idx) are read from the partial grad2d of every rank whose cyclic band its rectangle meets (NVLink peer loads)
+// and added in ascending rank order, exactly what sgr_gather_grad2d produced as a separate pass.
+template <bool STAGED, bool GATHER = false>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
-    const FrameDev f, const float *__restrict__ means3D, const float *__restrict__ shs, const float *__restrict__ colors_precomp,
+    const FrameDev f, const PeerTable pt, const float *__restrict__ means3D, const float *__restrict__ shs, const float *__restrict__ colors_precomp,
     const float *__restrict__ scales, const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
     const int32_t *__restrict__ radii, const GaussRec *__restrict__ rec, const float *__restrict__ grad2d,
     float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D, float *__restrict__ dL_dsh, float *__restrict__ dL_dcolors,
@@ -80,9 +83,27 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 
 	float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, g2v = g0v;
 	if (in_range) {
-		g0v = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
-		g1v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
-		g2v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
+		if (GATHER) {
+			if (visible) {
+				int x0, y0, x1, y1;
+				const float4 q0 = rec[idx].q0;
+				tile_rect(q0.x, q0.y, radii[idx], f.gx, f.gy, x0, y0, x1, y1);
+				const uint32_t mask = x1 > x0 ? touched_ranks(y0, y1, pt.world) : 0u;
+				const size_t g = (size_t)pt.rank * (size_t)pt.chunk + i;
+				for (int p = 0; p < pt.world; p++) {
+					if (!((mask >> p) & 1u)) continue;
+					const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + g * 12);
+					const float4 a = src[0], b = src[1], c = src[2];
+					g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
+					g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
+					g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
+				}
+			}
+		} else {
+			g0v = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
+			g1v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
+			g2v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
+		}
 		dL_dmeans2D[3 * i] = g0v.x; dL_dmeans2D[3 * i + 1] = g0v.y; dL_dmeans2D[3 * i + 2] = g0v.z;
 		dL_dopacity[i] = g1v.z;
 		if (dL_dcolors) { dL_dcolors[3 * i] = g1v.w; dL_dcolors[3 * i + 1] = g2v.x; dL_dcolors[3 * i + 2] = g2v.y; }
@@ -349,14 +370,39 @@ cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const
 		cudaError_t e = ensure_dynamic_smem(preprocess_bwd_kernel<true>, (int)smem, configured);
 		if (e != cudaSuccess) return e;
 		count_launch();
-		preprocess_bwd_kernel<true><<<(f.P + 255) / 256, 256, smem, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
+		preprocess_bwd_kernel<true><<<(f.P + 255) / 256, 256, smem, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
 		                                                                  radii, g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 		                                                                  dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
 	} else {
 		count_launch();
-		preprocess_bwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
+		preprocess_bwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
 		                                                               radii, g.rec, grad2d, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 		                                                               dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_preprocess_bwd_gather(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
+                                         const float *colors_precomp, const float *scales, const float *rotations,
+                                         const float *cov3D_precomp, const int32_t *radii, const GaussRec *rec, float *dL_dmeans3D,
+                                         float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
+                                         float *dL_drot, float *dL_dcov3D, cudaStream_t st) {
+	if (f.P == 0) return cudaSuccess;
+	const bool staged = shs != nullptr && f.M <= 16;
+	if (staged) {
+		const size_t smem = (size_t)8 * 32 * kShRow * sizeof(float);
+		static std::atomic<uint64_t> configured{0};
+		cudaError_t e = ensure_dynamic_smem(preprocess_bwd_kernel<true, true>, (int)smem, configured);
+		if (e != cudaSuccess) return e;
+		count_launch();
+		preprocess_bwd_kernel<true, true><<<(f.P + 255) / 256, 256, smem, st>>>(f, pt, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
+		                                                                        radii, rec, nullptr, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+		                                                                        dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
+	} else {
+		count_launch();
+		preprocess_bwd_kernel<false, true><<<(f.P + 255) / 256, 256, 0, st>>>(f, pt, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
+		                                                                      radii, rec, nullptr, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+		                                                                      dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
 	}
 	return cudaGetLastError();
 }

@@ -157,8 +157,11 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float
 }
 
 // COUNT = false: records + radii only (sgr_project; the tile counts are taken after the all-gather, per band)
-template <bool COUNT>
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, const float *__restrict__ means3D,
+// SCATTER = true (with COUNT = false): sgr_sharded_forward — the record additionally goes straight from registers into the
+// gathered arrays of exactly the ranks whose cyclic tile-row band its 3-sigma rectangle meets (NVLink peer stores), and the
+// radius (0 = "not yours") to every rank; threads f.P .. pt.chunk-1 are the padding slots of this rank's chunk.
+template <bool COUNT, bool SCATTER = false>
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, const PeerTable pt, const float *__restrict__ means3D,
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,
                                                              const float *__restrict__ opacities, const float *__restrict__ scales,
                                                              const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
@@ -193,8 +196,22 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 			r.q1 = make_float4(pr.conic.z, opacity, -0.5f * cp.qmax, pr.depth);
 			r.q2 = make_float4(rgb.x, rgb.y, rgb.z, __uint_as_float(clamp_bits));
 			rec[idx] = r;
+			if (SCATTER) {
+				const uint32_t mask = touched_ranks(pr.y0, pr.y1, pt.world);
+				const size_t g = (size_t)pt.rank * (size_t)pt.chunk + (size_t)idx;
+				for (int p = 0; p < pt.world; p++)
+					if ((mask >> p) & 1u) pt.rec[p][g] = r;
+			}
 		}
 		radii[idx] = pr.radius;
+	}
+	if (SCATTER) {
+		if ((long long)idx < pt.chunk) {
+			const uint32_t mask = pr.ok ? touched_ranks(pr.y0, pr.y1, pt.world) : 0u;
+			const size_t g = (size_t)pt.rank * (size_t)pt.chunk + (size_t)idx;
+			for (int p = 0; p < pt.world; p++) pt.radii[p][g] = ((mask >> p) & 1u) ? pr.radius : 0;
+			if (!in_range) radii[idx] = 0;  // padding slot of the local arrays
+		}
 	}
 	if (!COUNT) return;
 	uint32_t count = 0;
@@ -235,7 +252,7 @@ cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
 	count_launch();
-	preprocess_fwd_kernel<true><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
+	preprocess_fwd_kernel<true><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities, scales, rotations,
 	                                                                  cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
 	return cudaGetLastError();
 }
@@ -244,8 +261,18 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
                            int32_t *radii, GaussRec *rec, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
 	count_launch();
-	preprocess_fwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, means3D, shs, colors_precomp, opacities, scales, rotations,
+	preprocess_fwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities, scales, rotations,
 	                                                                   cov3D_precomp, radii, rec, nullptr, nullptr, nullptr);
+	return cudaGetLastError();
+}
+cudaError_t launch_project_scatter(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
+                                   const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
+                                   const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, cudaStream_t st) {
+	if (pt.chunk == 0) return cudaSuccess;
+	count_launch();
+	preprocess_fwd_kernel<false, true><<<(unsigned)((pt.chunk + 255) / 256), 256, 0, st>>>(f, pt, means3D, shs, colors_precomp, opacities, scales,
+	                                                                                       rotations, cov3D_precomp, radii_local, rec_local,
+	                                                                                       nullptr, nullptr, nullptr);
 	return cudaGetLastError();
 }
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,

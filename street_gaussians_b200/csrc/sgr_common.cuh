@@ -37,8 +37,10 @@ struct GeomView {
 	uint32_t *perm;           // Gaussian indices in ascending (depth, index) order
 	uint32_t *offsets;        // inclusive scan of tiles_touched[perm[.]]  (depth order)
 	uint32_t *big_list;       // depth-order positions of Gaussians whose rectangle is emitted by a whole warp (emit_big_kernel)
-	uint32_t *big_count;      // [0] number of entries in big_list (device counter, zeroed per forward)
-	                          // [1] instance count R of the last forward, [2] overflow flag, [3] instances actually emitted (bounded mode)
+	uint32_t *big_count;      // status words, zeroed per forward: [0] number of entries in big_list (device counter)
+	                          // [1] instance count R, [2] overflow bits (1 = instance capacity, 2 = Gaussian capacity of the compacted
+	                          // depth order), [3] instances actually emitted (bounded mode), [4] Gaussians with instances (compacted mode)
+	uint32_t *ckey, *cval;    // compacted depth-sort input (keys / Gaussian indices), Gaussian-sharded forward only
 	void *temp;               // cub temp storage: max(scan, depth sort)
 	size_t temp_bytes;
 	size_t total_bytes;
@@ -173,7 +175,7 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
-cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
+cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st, int64_t cap_v = -1, int *n_order = nullptr);
 // Gaussian-sharded exchange over peer memory (peer_exchange.cu); device copy of include/sgr.h's SgrPeers
 constexpr int kMaxPeers = 16;
 struct PeerTable {
@@ -182,25 +184,46 @@ struct PeerTable {
 	GaussRec *rec[kMaxPeers];
 	int32_t *radii[kMaxPeers];
 	const float *grad2d[kMaxPeers];
+	uint32_t *flags[kMaxPeers];  // rank p's barrier pad: u32[kMaxPeers], slot q = last epoch at which rank q arrived
 };
+// ranks whose cyclic band (row r -> rank r % world) meets tile rows [y0, y1)
+__device__ __forceinline__ uint32_t touched_ranks(int y0, int y1, int world) {
+	if (y1 <= y0) return 0u;
+	if (y1 - y0 >= world) return world >= 32 ? 0xffffffffu : ((1u << world) - 1u);
+	uint32_t m = 0u;
+	for (int y = y0; y < y1; y++) m |= 1u << (y % world);
+	return m;
+}
+cudaError_t launch_peer_barrier(const PeerTable &pt, uint32_t epoch, uint32_t *status, cudaStream_t st);
+// sgr_project fused with sgr_scatter_records: one pass over the rank's chunk (f.P local Gaussians, pt.chunk slots)
+cudaError_t launch_project_scatter(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
+                                   const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
+                                   const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, cudaStream_t st);
+// sgr_gather_grad2d fused into sgr_backward_geom: the 12 screen-space sums of each local Gaussian are summed from the ranks
+// that rendered it while the chain rule runs
+cudaError_t launch_preprocess_bwd_gather(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
+                                         const float *colors_precomp, const float *scales, const float *rotations,
+                                         const float *cov3D_precomp, const int32_t *radii, const GaussRec *rec, float *dL_dmeans3D,
+                                         float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
+                                         float *dL_drot, float *dL_dcov3D, cudaStream_t st);
 cudaError_t launch_scatter_records(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, cudaStream_t st);
 cudaError_t launch_gather_grad2d(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, float *out,
                                  cudaStream_t st);
 // Gaussian-sharded mode: tile counts / depth keys of gathered records against this rank's band (binning.cu)
-cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st);
+cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st, float *zero_rows = nullptr);
 size_t geom_temp_bytes(int P);
 size_t sort_temp_bytes(int64_t R);
 // cap < 0: exact mode, R is the host-known instance count.  cap >= 0: bounded mode, R is ignored, the arrays hold `cap`
 // slots and the true count lives in g.big_count[1..3].
 cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, BinView b, ImgView img, int64_t R,
-                           cudaStream_t st, int64_t cap = -1);
+                           cudaStream_t st, int64_t cap = -1, int n_order = -1);
 cudaError_t launch_blend_fwd(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *semantics, float *out_color,
                              float *out_depth, float *out_alpha, float *out_sem, cudaStream_t st);
 cudaError_t launch_blend_bwd(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *semantics,
                              const float *out_alpha, const float *dL_dcolor, const float *dL_ddepth, const float *dL_dalpha,
-                             const float *dL_dsem, float *grad2d, float *dL_dsemantics, cudaStream_t st);
+                             const float *dL_dsem, float *grad2d, float *dL_dsemantics, cudaStream_t st, bool grad2d_zeroed = false);
 cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *out_alpha, const float *dL_dcolor,
-                              const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st);
+                              const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st, bool grad2d_zeroed = false);
 cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
                                   const float *scales, const float *rotations, const float *cov3D_precomp,
                                   const int32_t *radii, GeomView g, const float *grad2d, float *dL_dmeans3D,

@@ -104,7 +104,8 @@ class InstanceCapacity:
 
     def __init__(self, headroom: float = 1.25, initial: Optional[int] = None):
         self.headroom, self.capacity = float(headroom), (int(initial) if initial else None)
-        self._pending = []  # (pinned int32[2], cuda event) in submission order
+        self.gaussian_capacity = None  # depth-order slots of the compacted Gaussian-sharded forward (sgr_sharded_forward)
+        self._pending = []  # (pinned int32[4], cuda event) in submission order
         self._pool = []     # pinned status words ready for reuse: no pin_memory() (a cudaHostAlloc) inside the steady-state step
 
     def observe(self, R: int):
@@ -112,9 +113,14 @@ class InstanceCapacity:
         if self.capacity is None or want > self.capacity:
             self.capacity = want
 
+    def observe_gaussians(self, n: int):
+        want = int(n * self.headroom) + 1024
+        if self.gaussian_capacity is None or want > self.gaussian_capacity:
+            self.gaussian_capacity = want
+
     def status_word(self) -> torch.Tensor:
-        """A pinned int32[2] for sgr_forward_status_async; recycled once its frame has been checked."""
-        return self._pool.pop() if self._pool else torch.zeros(2, dtype=torch.int32).pin_memory()
+        """A pinned int32[4] for sgr_forward_status_async; recycled once its frame has been checked."""
+        return self._pool.pop() if self._pool else torch.zeros(4, dtype=torch.int32).pin_memory()
 
     def track(self, host_status: torch.Tensor, event):
         self._pending.append((host_status, event))
@@ -131,14 +137,17 @@ class InstanceCapacity:
             if not ev.query():
                 self._pending.append((host_status, ev))
                 continue
-            R, overflow = int(host_status[0]), int(host_status[1])
+            R, overflow, n_sel = int(host_status[0]), int(host_status[1]), int(host_status[3])
             self._pool.append(host_status)
-            old = self.capacity
+            old, old_g = self.capacity, self.gaussian_capacity
             self.observe(R)
+            if n_sel:
+                self.observe_gaussians(n_sel)
             if overflow:
                 self._pending.extend(pending[i + 1:])
-                raise _capi.SgrError(f"instance capacity {old} overflowed (frame needed {R}); capacity raised to {self.capacity} — "
-                                     "re-render that frame")
+                what = (f"instance capacity {old} overflowed (frame needed {R}); capacity raised to {self.capacity}" if overflow & 1 else
+                        f"Gaussian capacity {old_g} overflowed (band holds {n_sel}); capacity raised to {self.gaussian_capacity}")
+                raise _capi.SgrError(what + " — re-render that frame")
 
 
 def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,

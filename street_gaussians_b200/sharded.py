@@ -238,29 +238,37 @@ class PeerWorkspace:
         self.chunk, self.world, self.rank, self.P_total = int(chunk), int(world), int(rank), int(chunk) * int(world)
         if world > _capi.MAX_PEERS:
             raise _capi.SgrError(f"peer exchange supports at most {_capi.MAX_PEERS} ranks, got {world}")
-        self.geom_bytes, self.img_bytes, self.off_radii, self.off_grad, self.total = self.layout(settings, self.P_total, device)
+        self.geom_bytes, self.img_bytes, self.off_radii, self.off_grad, self.off_flags, self.total = self.layout(settings, self.P_total, device)
         self.hdl = None
         self.in_flight = False  # a differentiable forward has used the buffers and its backward has not run yet
+        self.epoch = 0          # epoch of the last sgr_peer_barrier issued on this workspace (every rank counts alike)
+        self.fwd_pending = False  # the last fused call was a forward: the next forward needs a leading barrier (see sgr.h)
+        self._step_bufs = None
         if _buffers is not None:  # single-process emulation: (my buffer, base pointers of all ranks' buffers)
             self.buf, ptrs = _buffers
         else:
             import torch.distributed._symmetric_memory as symm
             self.buf = symm.empty(self.total, dtype=torch.uint8, device=device)
+            self.buf[self.off_flags:].zero_()  # barrier pads start at epoch 0
             self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
             ptrs = list(self.hdl.buffer_ptrs)
+            self.hdl.barrier(channel=0)  # every pad is zero before any rank can send its first epoch
         self.geom = self.buf[: self.geom_bytes]
         self.radii_all = self.buf[self.off_radii: self.off_radii + 4 * self.P_total].view(torch.int32)
         self.grad2d = self.buf[self.off_grad: self.off_grad + 48 * self.P_total].view(torch.float32).view(self.P_total, 12)
+        if _buffers is not None:
+            self.buf[self.off_flags:].zero_()
         self.peers = _capi.SgrPeers()
         self.peers.world, self.peers.rank, self.peers.chunk = self.world, self.rank, self.chunk
         for p in range(self.world):
             self.peers.records[p] = ptrs[p]
             self.peers.radii[p] = ptrs[p] + self.off_radii
             self.peers.grad2d[p] = ptrs[p] + self.off_grad
+            self.peers.flags[p] = ptrs[p] + self.off_flags
 
     @staticmethod
     def layout(settings, P_total: int, device):
-        """(geom_bytes, img_bytes, offset of radii_all, offset of grad2d, total bytes) of the per-rank buffer."""
+        """(geom_bytes, img_bytes, offset of radii_all, offset of grad2d, offset of the barrier pad, total bytes) of the per-rank buffer."""
         L = _capi.lib()
         fr, keep = _make_frame(settings, P_total, 0, 0, device, None)
         gb, ib = C.c_size_t(0), C.c_size_t(0)
@@ -268,19 +276,40 @@ class PeerWorkspace:
         del keep
         off_radii = _align(gb.value)
         off_grad = _align(off_radii + 4 * P_total)
-        return gb.value, ib.value, off_radii, off_grad, off_grad + 48 * P_total
+        off_flags = _align(off_grad + 48 * P_total)
+        return gb.value, ib.value, off_radii, off_grad, off_flags, off_flags + 256
 
     @classmethod
     def emulate(cls, settings, chunk: int, world: int, device):
         """`world` workspaces on ONE device whose peer tables point at each other (tests; world == 1 module path)."""
-        total = cls.layout(settings, int(chunk) * int(world), device)[4]
+        total = cls.layout(settings, int(chunk) * int(world), device)[5]
         bufs = [torch.empty(total, dtype=torch.uint8, device=device) for _ in range(world)]
         ptrs = [b.data_ptr() for b in bufs]
         return [cls(settings, chunk, world, r, device, _buffers=(bufs[r], ptrs)) for r in range(world)]
 
     def barrier(self):
+        """Device-side barrier of the STAGED path (torch symmetric memory's signal pad)."""
         if self.hdl is not None:
             self.hdl.barrier(channel=0)
+
+    def next_epochs(self, n: int = 1) -> int:
+        """Reserve `n` consecutive barrier epochs of the fused path; returns the LAST one."""
+        self.epoch += n
+        return self.epoch
+
+    def step_buffers(self, capacity_bytes: int):
+        """Buffers that live from a fused forward to its backward.  One forward is in flight per workspace, so they are
+        allocated once (and re-grown with the instance capacity) instead of once per step."""
+        dev = self.buf.device
+        b = self._step_bufs
+        if b is None:
+            b = dict(rec=torch.empty((self.chunk, REC_FLOATS), device=dev, dtype=torch.float32),
+                     radii=torch.empty((self.chunk,), device=dev, dtype=torch.int32),
+                     img=torch.empty((self.img_bytes,), device=dev, dtype=torch.uint8), binning=None)
+            self._step_bufs = b
+        if b["binning"] is None or b["binning"].numel() < capacity_bytes:
+            b["binning"] = torch.empty((capacity_bytes,), device=dev, dtype=torch.uint8)
+        return b
 
 
 def scatter_records(settings, ws: PeerWorkspace, rec_local, radii_local, P_local: int):
@@ -324,16 +353,25 @@ class _GaussianShardedRasterize(torch.autograd.Function):
         device, P = means3D.device, int(means3D.shape[0])
         world, chunk, group = owner.world, owner.chunk_for(P), owner.group
         S = int(tensors["semantics"].shape[1]) if tensors["semantics"] is not None else 0
-        rec, radii = project_records(tensors, settings, chunk)
         P_total = chunk * world
         ws = owner.workspace(device) if owner.exchange == "p2p" else None
         sem_all = None
+        cap = owner.capacity
+        if ws is not None and owner.fused and S == 0 and cap is not None and cap.capacity is not None:
+            return _fused_forward(ctx, tensors, settings, owner, ws, P, chunk, differentiable,
+                                  (means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp))
+        rec, radii = project_records(tensors, settings, chunk)
         if ws is not None:  # records go straight into the peers' gathered arrays over NVLink
             if ws.in_flight:
                 raise _capi.SgrError("GaussianShardedRasterizer(exchange='p2p') owns ONE peer workspace: run backward() of the previous "
                                      "forward (or call release_workspace()) before the next forward, or use one rasterizer per camera")
+            if ws.fwd_pending:
+                # the previous forward on this workspace had no backward (eval / no_grad loop): a peer may still be counting,
+                # emitting or blending from the records this scatter overwrites — only the backward barrier orders that
+                ws.barrier()
             scatter_records(settings, ws, rec, radii, P)
             ws.barrier()
+            ws.fwd_pending = True
             st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
         else:
             st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
@@ -367,6 +405,8 @@ class _GaussianShardedRasterize(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha, grad_semantic):
+        if getattr(ctx, "fused", False):
+            return _fused_backward(ctx, grad_color, grad_depth, grad_alpha)
         rec, radii, alpha = ctx.saved_tensors
         settings, owner, st, tensors, shapes = ctx.settings, ctx.owner, ctx.state, ctx.tensors, ctx.shapes
         dev = alpha.device
@@ -383,6 +423,7 @@ class _GaussianShardedRasterize(torch.autograd.Function):
                                                grad_alpha, grad_semantic, grad2d_out=ws.grad2d if ws is not None else None)
         if ws is not None:  # pull the partial rows of the own Gaussians from the ranks that rendered them
             ws.barrier()
+            ws.fwd_pending = False
             grad2d = gather_grad2d(settings, ws, rec, radii, P)
             ws.in_flight = False  # stream order protects the buffers from here on: the next forward is enqueued after the gather
             if owner.world > 1 and S > 0:
@@ -415,6 +456,116 @@ class _GaussianShardedRasterize(torch.autograd.Function):
                 fit(g_opac, 5), fit(g_scales, 6), fit(g_rots, 7), fit(g_cov, 8), None, None, None)
 
 
+def sharded_forward_raw(settings, band, ws: "PeerWorkspace", tensors, P: int, capacity: int, gaussian_capacity: int, status_word=None):
+    """One sgr_sharded_forward call on the current stream (used by the autograd path and, with emulated workspaces on
+    separate streams, by the single-GPU tests).  Returns (color, depth, alpha, step buffers)."""
+    L = _capi.lib()
+    device = tensors["means3D"].device
+    H, W = int(settings.image_height), int(settings.image_width)
+    nbytes = int(L.sgr_binning_bytes(capacity))
+    bufs = ws.step_buffers(nbytes)
+    z = lambda c: torch.zeros((c, H, W), device=device, dtype=torch.float32)  # foreign rows stay zero
+    color, depth, alpha = z(3), z(1), z(1)  # (separate tensors: autograd outputs that are views of one base cannot be modified in place)
+    M = int(tensors["sh"].shape[1]) if tensors["sh"] is not None else 0
+    fr, keep = _make_frame(settings, P, M, 0, device, band)
+    pre = 1 if ws.fwd_pending else 0
+    epoch = ws.next_epochs(1 + pre)
+    with torch.cuda.device(device):
+        rc = L.sgr_sharded_forward(C.byref(fr), C.byref(ws.peers), _ptr(tensors["means3D"]), _ptr(tensors["sh"]), _ptr(tensors["colors_precomp"]),
+                                   _ptr(tensors["opacities"]), _ptr(tensors["scales"]), _ptr(tensors["rotations"]), _ptr(tensors["cov3Ds_precomp"]),
+                                   _ptr(color), _ptr(depth), _ptr(alpha), _ptr(bufs["radii"]), _ptr(bufs["rec"]), ws.geom_bytes,
+                                   _ptr(bufs["img"]), ws.img_bytes, _ptr(bufs["binning"]), nbytes, capacity, gaussian_capacity, epoch, pre,
+                                   _stream(device))
+        _capi.check(rc, "sgr_sharded_forward")
+        if status_word is not None:
+            frt, keep2 = _make_frame(settings, ws.P_total, 0, 0, device, band)
+            rc = L.sgr_forward_status_async(C.byref(frt), _ptr(ws.geom), C.c_void_p(status_word.data_ptr()), _stream(device))
+            _capi.check(rc, "sgr_forward_status_async")
+            del keep2
+    del keep
+    ws.fwd_pending = True
+    return color, depth, alpha, bufs
+
+
+def sharded_backward_raw(settings, band, ws: "PeerWorkspace", tensors, P: int, capacity: int, alpha, gc, gd, ga):
+    """One sgr_sharded_backward call on the current stream.  Returns the 8 gradients in _backward_geom_impl's order."""
+    L = _capi.lib()
+    dev = alpha.device
+    sh, colors, scales, rots, cov = (tensors[k] for k in ("sh", "colors_precomp", "scales", "rotations", "cov3Ds_precomp"))
+    M = int(sh.shape[1]) if sh is not None else 0
+    e = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    g_means3D, g_means2D, g_opac = e(P, 3), e(P, 3), e(P, 1)
+    g_sh = e(P, M, 3) if sh is not None else None
+    g_colors = e(P, 3) if colors is not None else None
+    g_scales = e(P, 3) if cov is None else None
+    g_rots = e(P, 4) if cov is None else None
+    g_cov = e(P, 6) if cov is not None else None
+    bufs = ws.step_buffers(0)
+    fr, keep = _make_frame(settings, P, M, 0, dev, band)
+    epoch = ws.next_epochs(1)
+    with torch.cuda.device(dev):
+        rc = L.sgr_sharded_backward(C.byref(fr), C.byref(ws.peers), capacity, _ptr(tensors["means3D"]), _ptr(sh), _ptr(colors), _ptr(scales),
+                                    _ptr(rots), _ptr(cov), _ptr(bufs["radii"]), _ptr(bufs["rec"]), _ptr(bufs["img"]), _ptr(bufs["binning"]),
+                                    _ptr(alpha), _ptr(gc), _ptr(gd), _ptr(ga), _ptr(g_means3D), _ptr(g_means2D), _ptr(g_sh), _ptr(g_colors),
+                                    _ptr(g_opac), _ptr(g_scales), _ptr(g_rots), _ptr(g_cov), epoch, _stream(dev))
+    _capi.check(rc, "sgr_sharded_backward")
+    del keep
+    ws.fwd_pending = False  # every rank passed the backward barrier after its blend_bwd: the records may be overwritten
+    return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov
+
+
+def _fused_forward(ctx, tensors, settings, owner, ws: "PeerWorkspace", P: int, chunk: int, differentiable: bool, inputs):
+    """sgr_sharded_forward: project + scatter, barrier, bin / sort / blend in ONE C-ABI call (no host work between the ~28 launches)."""
+    device = tensors["means3D"].device
+    if ws.in_flight:
+        raise _capi.SgrError("GaussianShardedRasterizer(exchange='p2p') owns ONE peer workspace: run backward() of the previous "
+                             "forward (or call release_workspace()) before the next forward, or use one rasterizer per camera")
+    cap = owner.capacity
+    cap.check()
+    H, W = int(settings.image_height), int(settings.image_width)
+    capacity = int(cap.capacity)
+    # depth-order slots: learnt from the previous frames (status word 4); the first fused frame compacts into all slots
+    gcap = int(cap.gaussian_capacity) if cap.gaussian_capacity is not None else ws.P_total
+    host_status = cap.status_word()
+    color, depth, alpha, bufs = sharded_forward_raw(settings, owner.band, ws, tensors, P, capacity, gcap, host_status)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    cap.track(host_status, ev)
+    ws.in_flight = bool(differentiable)
+    ctx.fused, ctx.settings, ctx.owner, ctx.ws, ctx.P, ctx.capacity, ctx.tensors = True, settings, owner, ws, P, capacity, tensors
+    ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype) for t in inputs)
+    ctx.save_for_backward(alpha)
+    radii_out = bufs["radii"][:P]
+    ctx.mark_non_differentiable(radii_out)
+    return color, radii_out, depth, alpha, torch.zeros((0, H, W), device=device, dtype=torch.float32)
+
+
+def _fused_backward(ctx, grad_color, grad_depth, grad_alpha):
+    """sgr_sharded_backward: blend_bwd, barrier, chain rule with the peer gather folded in — ONE C-ABI call."""
+    (alpha,) = ctx.saved_tensors
+    settings, owner, ws, P, tensors, shapes = ctx.settings, ctx.owner, ctx.ws, ctx.P, ctx.tensors, ctx.shapes
+    dev = alpha.device
+    H, W = int(settings.image_height), int(settings.image_width)
+    zimg = lambda c: torch.zeros((c, H, W), device=dev, dtype=torch.float32)
+    gc = _dev_f32(grad_color, dev) if grad_color is not None else zimg(3)
+    gd = _dev_f32(grad_depth, dev) if grad_depth is not None else zimg(1)
+    ga = _dev_f32(grad_alpha, dev) if grad_alpha is not None else zimg(1)
+    g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov = sharded_backward_raw(settings, owner.band, ws, tensors, P,
+                                                                                                   ctx.capacity, alpha, gc, gd, ga)
+    ws.in_flight = False
+
+    def fit(t, i):
+        if shapes[i] is None:
+            return None
+        shape, device, dtype = shapes[i]
+        if t is None:
+            return torch.zeros(shape, device=device, dtype=dtype)
+        return t.reshape(shape).to(device=device, dtype=dtype)
+
+    return (fit(g_means3D, 0), fit(g_means2D, 1), fit(g_sh, 2), fit(g_colors, 3), fit(None, 4), fit(g_opac, 5), fit(g_scales, 6),
+            fit(g_rots, 7), fit(g_cov, 8), None, None, None)
+
+
 class GaussianShardedRasterizer(nn.Module):
     """Same call signature as GaussianRasterizer.forward, but every argument holds only THIS rank's Gaussians and the
     returned radii / gradients cover only them; the images cover this rank's tile rows (zeros elsewhere).  The gathered
@@ -423,7 +574,7 @@ class GaussianShardedRasterizer(nn.Module):
 
     def __init__(self, raster_settings: GaussianRasterizationSettings, group: Optional[dist.ProcessGroup] = None,
                  layout: str = "cyclic", capacity: Optional[InstanceCapacity] = None, chunk: Optional[int] = None,
-                 exchange: str = "nccl"):
+                 exchange: str = "nccl", fused: bool = True):
         """exchange = "nccl": all-gather of records / reduce-scatter of grad2d.  exchange = "p2p": each record is stored
         over NVLink into the gathered arrays of only the ranks whose band it touches and the grad2d rows are read back
         from them (PeerWorkspace; needs torch symmetric memory and the cyclic layout).  With "p2p" the rasterizer owns ONE
@@ -434,6 +585,10 @@ class GaussianShardedRasterizer(nn.Module):
         if exchange == "p2p" and layout != "cyclic":
             raise ValueError("the peer-memory exchange needs the cyclic tile-row layout")
         self.exchange, self._ws = exchange, None
+        # exchange="p2p" with a capacity object (sync-free binning) and no feature channels runs the whole forward / backward as
+        # ONE C-ABI call each (sgr_sharded_forward / sgr_sharded_backward) once the capacity is known; fused=False keeps the
+        # staged calls (one per step of include/sgr.h's list)
+        self.fused = bool(fused)
         self.raster_settings, self.group, self.capacity = raster_settings, group, capacity
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0

@@ -363,6 +363,101 @@ def test_gaussian_sharded_emulated_ranks_match_single_gpu(S, world, layout):
             assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, i
 
 
+@pytest.mark.parametrize("world,compact", [(3, True), (2, False), (4, True)])
+def test_fused_sharded_step_emulated_ranks(world, compact):
+    """sgr_sharded_forward / sgr_sharded_backward (ONE C-ABI call each: project+scatter, device barrier, compacted depth sort, bin,
+    blend | blend_bwd, device barrier, chain rule with the peer gather folded in) with the N ranks' workspaces on ONE GPU.  Each
+    rank runs on its own stream — the barrier kernels of the ranks must be co-resident, exactly as on N GPUs.  Two consecutive
+    frames (the second one exercises epoch bookkeeping, the in-forward zeroing of the grad2d rows and stale data of the first);
+    images bit-identical to the single-GPU render, gradients equal up to float summation order."""
+    from street_gaussians_b200 import rasterizer as R
+    from street_gaussians_b200 import sharded as SH
+    P, H, W = 40_003, 608, 800
+    dev = torch.device("cuda")
+    frames = [synthetic.make_scene(P=P, width=W, height=H, sh_degree=3, seed=60 + i, pose=True) for i in range(2)]
+    chunk = (P + world - 1) // world
+    st0 = util.settings_from(sgb, frames[0]["cam"], dev)
+    wss = SH.PeerWorkspace.emulate(st0, chunk, world, dev)
+    for ws in wss:
+        ws.buf[: ws.off_flags].fill_(0x7f)  # poison everything but the barrier pads
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    L = _capi.lib()
+    for fi, scene in enumerate(frames):
+        st = util.settings_from(sgb, scene["cam"], dev)
+        t = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations", "grad_color", "grad_depth", "grad_alpha")}
+        with torch.no_grad():
+            col, rad, dep, alp, se, fst, tens = R._forward_impl(t["means3D"], t["shs"], None, None, t["opacities"], t["scales"], t["rotations"],
+                                                               None, st, None)
+            g2d, _ = R._backward_blend_impl(st, None, fst, tens, alp, t["grad_color"], t["grad_depth"], t["grad_alpha"], None)
+            ref_grads = R._backward_geom_impl(st, None, fst, tens, rad, g2d)
+            torch.cuda.synchronize()
+            capacity = int(fst.num_instances) + 1000  # every band fits
+            local, outs, status = [], [], []
+            for r in range(world):
+                sl = slice(r * chunk, min(P, (r + 1) * chunk))
+                local.append(SH._local_tensors(t["means3D"][sl], t["shs"][sl], None, None, t["opacities"][sl], t["scales"][sl],
+                                               t["rotations"][sl], None))
+                status.append(torch.zeros(4, dtype=torch.int32).pin_memory())
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    P_r = int(local[r]["means3D"].shape[0])
+                    gcap = (chunk * world) // 2 if compact else -1
+                    outs.append(SH.sharded_forward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], P_r, capacity, gcap, status[r]))
+            torch.cuda.synchronize()
+            imgs = [sum(o[i] for o in outs) for i in range(3)]
+            for a, b, name in zip(imgs, (col, dep, alp), ("color", "depth", "alpha")):
+                assert torch.equal(a, b), f"frame {fi}: {name} differs from the single-GPU render"
+            n_sel_total = 0
+            for r in range(world):
+                R_r, over, emitted, n_sel = (int(v) for v in status[r])
+                assert over == 0 and R_r == emitted and R_r <= fst.num_instances
+                assert (n_sel > 0) == compact
+                n_sel_total += n_sel
+                assert torch.equal(outs[r][3]["radii"][: int(local[r]["means3D"].shape[0])], rad[r * chunk: min(P, (r + 1) * chunk)])
+            if compact:
+                assert n_sel_total < 0.8 * world * int((rad > 0).sum())  # each band sorts its own Gaussians, not all of them
+            grads = []
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    P_r = int(local[r]["means3D"].shape[0])
+                    grads.append(SH.sharded_backward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], P_r, capacity, outs[r][2],
+                                                         t["grad_color"], t["grad_depth"], t["grad_alpha"]))
+            torch.cuda.synchronize()
+            for i, ref in enumerate(ref_grads):
+                if ref is None:
+                    assert all(g[i] is None for g in grads)
+                    continue
+                got = torch.cat([g[i] for g in grads])
+                assert got.shape == ref.shape
+                assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, (fi, i)
+    # a forward that follows a forward (no backward): the leading barrier of sgr.h is taken (epochs advance by 2)
+    with torch.no_grad():
+        e0 = [ws.epoch for ws in wss]
+        for rep in range(2):
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    SH.sharded_forward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], int(local[r]["means3D"].shape[0]), capacity, -1)
+        torch.cuda.synchronize()
+        assert [ws.epoch - e for ws, e in zip(wss, e0)] == [3] * world
+
+
+def test_gaussian_capacity_overflow_is_flagged():
+    """More Gaussians in the band than depth-order slots: overflow bit 2, no out-of-bounds write (the sort covers cap slots)."""
+    from street_gaussians_b200 import sharded as SH
+    P, H, W = 20_000, 304, 400
+    dev = torch.device("cuda")
+    scene = synthetic.make_scene(P=P, width=W, height=H, sh_degree=1, seed=70, pose=True)
+    st = util.settings_from(sgb, scene["cam"], dev)
+    ws = SH.PeerWorkspace.emulate(st, P, 1, dev)[0]
+    lt = SH._local_tensors(scene["means3D"].to(dev), scene["shs"].to(dev), None, None, scene["opacities"].to(dev), scene["scales"].to(dev),
+                           scene["rotations"].to(dev), None)
+    hs = torch.zeros(4, dtype=torch.int32).pin_memory()
+    with torch.no_grad():
+        SH.sharded_forward_raw(st, None, ws, lt, P, 2_000_000, 100, hs)
+    torch.cuda.synchronize()
+    assert int(hs[1]) & 2 and int(hs[3]) > 100
+
+
 @pytest.mark.parametrize("world", [2, 5])
 def test_gaussian_sharded_peer_exchange_emulated_ranks(world):
     """The NVLink peer-memory exchange (sgr_scatter_records / sgr_gather_grad2d) with the N ranks' workspaces living on ONE
@@ -520,6 +615,14 @@ def test_mark_visible_filter_and_knn():
         a = sgb.distCUDA2(big.to(dev)).cpu().numpy()
         b = rk.distCUDA2(big.to(dev)).cpu().numpy()
         assert (a == b).all(), "distCUDA2 must be bit-identical to simple-knn"
+        # visible_filter / markVisible against the reference's own entry points (_C.rasterize_gaussians_filter, _C.mark_visible)
+        ref = util.load_ref()
+        rr = ref.GaussianRasterizer(util.settings_from(ref, scene["cam"], dev))
+        r_radii, r_m2d = rr.visible_filter(scene["means3D"].to(dev), scales=scene["scales"].to(dev), rotations=scene["rotations"].to(dev))
+        assert torch.equal(radii, r_radii), "visible_filter radii must equal the reference's"
+        vv = r_radii > 0
+        assert torch.equal(m2d[vv], r_m2d[vv]), "visible_filter means2D must be bit-equal to the reference's for visible Gaussians"
+        assert torch.equal(vis, rr.markVisible(scene["means3D"].to(dev)))
 
 
 def test_direct_c_abi_error_paths():
