@@ -243,6 +243,45 @@ int sgr_sharded_backward(const SgrFrame *frame, const SgrPeers *peers, int64_t c
                          float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
                          float *dL_dscales, float *dL_drotations, float *dL_dcov3D, uint32_t barrier_epoch, void *stream);
 
+/* ---- Scene-graph composer (no native counterpart in the reference, which composes with ~40 PyTorch kernels) ----
+ * One call builds the rasterizer's inputs from the raw parameters of every sub-model of the scene graph, as
+ * StreetGaussianModel.get_xyz / get_rotation / get_scaling / get_opacity / get_features do
+ * (lib/models/street_gaussian_model.py:287-449 with the activations of lib/models/gaussian_model.py:224-251 and the Fourier DC
+ * colour of lib/models/gaussian_model_actor.py:71-80).  Segment s covers composed indices [start, start + count); segments must be
+ * listed in ascending, gap-free order (background first, then the actors of the frame, as the reference concatenates them). */
+#define SGR_MAX_FOURIER 8                 /* largest fourier_dim (cfg.model.gaussian.fourier_dim; 5 in the shipped configs) */
+#define SGR_MAX_SEGMENTS_PER_LAUNCH 32    /* larger tables are processed in groups of this many segments */
+typedef struct SgrSegment {
+	int32_t start, count;   /* range in the composed arrays */
+	int32_t fourier_dim;    /* rows of features_dc per Gaussian (1 for the background) */
+	int32_t posed;          /* 0: world-space model (background); 1: actor, posed by poses[s] with optional mirroring */
+	const float *xyz;            /* [count,3]      _xyz                                   (device) */
+	const float *rotation;       /* [count,4]      _rotation, raw (w,x,y,z)                        */
+	const float *scaling;        /* [count,3]      _scaling, log                                   */
+	const float *opacity;        /* [count,1]      _opacity, logit                                 */
+	const float *features_dc;    /* [count,C,3]    _features_dc                                    */
+	const float *features_rest;  /* [count,M-1,3]  _features_rest (NULL when M == 1)               */
+} SgrSegment;
+typedef struct SgrSegmentGrads {   /* where sgr_compose_backward writes the gradient of each raw array (same shapes; fully written) */
+	float *xyz, *rotation, *scaling, *opacity, *features_dc, *features_rest;
+} SgrSegmentGrads;
+/* segments: HOST array.  poses[num_segments,8] (device): actor -> world quaternion (w,x,y,z) as parse_camera leaves it in
+ * obj_rots (street_gaussian_model.py:258-273; NOT required to be unit) + translation + 1 pad float; rows of unposed segments are
+ * ignored.  idft[num_segments, SGR_MAX_FOURIER] (device): IDFT(t, C) row of each actor (lib/utils/sh_utils.py:120-130).
+ * flip (device, uint8 [P] indexed by composed id, or NULL): 1 = mirror this Gaussian across the actor's local x-z plane (the
+ * training-time symmetry augmentation, :275-284, 319-323, 347-349); flip_quat[4] (device) = the reference's flip_matrix.
+ * Outputs (device, fully written): means3D[P,3], rotations[P,4], scales[P,3], opacities[P,1], shs[P,M,3]. */
+int sgr_compose_forward(const SgrSegment *segments, int32_t num_segments, int32_t M, const float *poses, const float *idft,
+                        const uint8_t *flip, const float *flip_quat, float *means3D, float *rotations, float *scales, float *opacities,
+                        float *shs, void *stream);
+/* Gradients of the five composed arrays -> gradients of every raw array (grads: HOST array parallel to segments) and of the
+ * poses: dposes[num_segments,8] (device; rows of unposed segments are zero) — what autograd's expand / cat / einsum backward
+ * accumulates for obj_rots and obj_trans in the reference.  pose_scratch: num_segments*16 floats of device scratch. */
+int sgr_compose_backward(const SgrSegment *segments, const SgrSegmentGrads *grads, int32_t num_segments, int32_t M, const float *poses,
+                         const float *idft, const uint8_t *flip, const float *flip_quat, const float *dL_dmeans3D,
+                         const float *dL_drotations, const float *dL_dscales, const float *dL_dopacities, const float *dL_dshs,
+                         float *dposes, float *pose_scratch, void *stream);
+
 /* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
  * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */
 int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,

@@ -13,7 +13,9 @@ import sys
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, InstanceCapacity, TileRowBand,  # noqa: F401
                          distCUDA2, rasterize_gaussians)
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "TileRowBand", "InstanceCapacity", "rasterize_gaussians", "distCUDA2",
+from .composer import compose  # noqa: E402,F401
+
+__all__ = ["compose", "GaussianRasterizationSettings", "GaussianRasterizer", "TileRowBand", "InstanceCapacity", "rasterize_gaussians", "distCUDA2",
            "install_shims"]
 
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")

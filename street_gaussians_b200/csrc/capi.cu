@@ -577,6 +577,62 @@ int sgr_visible_filter(const SgrFrame *frame, const float *means3D, const float 
 	return SGR_OK;
 }
 
+static int check_segments(const SgrSegment *segs, int32_t n, int32_t M, int64_t &P) {
+	if (!segs || n <= 0) return fail(SGR_EINVAL, "segment table is empty");
+	if (M < 1 || M > 16) return fail(SGR_EINVAL, "M = %d SH coefficients per Gaussian (must be 1..16)", M);
+	int64_t at = segs[0].start;
+	if (at != 0) return fail(SGR_EINVAL, "segment 0 must start at composed index 0");
+	for (int k = 0; k < n; k++) {
+		const SgrSegment &s = segs[k];
+		if (s.start != at || s.count < 0) return fail(SGR_EINVAL, "segment %d: start %d (expected %lld), count %d — segments must be ascending and gap-free", k, s.start, (long long)at, s.count);
+		if (s.fourier_dim < 1 || s.fourier_dim > SGR_MAX_FOURIER) return fail(SGR_EINVAL, "segment %d: fourier_dim %d outside 1..%d", k, s.fourier_dim, SGR_MAX_FOURIER);
+		if (s.count > 0 && (!s.xyz || !s.rotation || !s.scaling || !s.opacity || !s.features_dc || (M > 1 && !s.features_rest)))
+			return fail(SGR_EINVAL, "segment %d has a NULL parameter array", k);
+		at += s.count;
+	}
+	if (at > 0x7fffffffLL) return fail(SGR_EUNSUPPORTED, "composed Gaussian count exceeds 2^31-1");
+	P = at;
+	return SGR_OK;
+}
+
+int sgr_compose_forward(const SgrSegment *segments, int32_t num_segments, int32_t M, const float *poses, const float *idft,
+                        const uint8_t *flip, const float *flip_quat, float *means3D, float *rotations, float *scales, float *opacities,
+                        float *shs, void *stream) {
+	int64_t P = 0;
+	int rc = check_segments(segments, num_segments, M, P);
+	if (rc) return rc;
+	if (P == 0) return SGR_OK;
+	if (!poses || !idft || !means3D || !rotations || !scales || !opacities || !shs) return fail(SGR_EINVAL, "NULL pointer passed to sgr_compose_forward");
+	if (flip && !flip_quat) return fail(SGR_EINVAL, "flip mask given without flip_quat");
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_compose_fwd(segments, num_segments, M, poses, idft, flip, flip_quat, means3D, rotations, scales, opacities, shs, st), "compose_fwd");
+	return SGR_OK;
+}
+
+int sgr_compose_backward(const SgrSegment *segments, const SgrSegmentGrads *grads, int32_t num_segments, int32_t M, const float *poses,
+                         const float *idft, const uint8_t *flip, const float *flip_quat, const float *dL_dmeans3D,
+                         const float *dL_drotations, const float *dL_dscales, const float *dL_dopacities, const float *dL_dshs,
+                         float *dposes, float *pose_scratch, void *stream) {
+	int64_t P = 0;
+	int rc = check_segments(segments, num_segments, M, P);
+	if (rc) return rc;
+	if (!grads || !dposes || !pose_scratch || !poses || !idft) return fail(SGR_EINVAL, "NULL pointer passed to sgr_compose_backward");
+	if (P > 0 && (!dL_dmeans3D || !dL_drotations || !dL_dscales || !dL_dopacities || !dL_dshs)) return fail(SGR_EINVAL, "NULL upstream gradient");
+	if (flip && !flip_quat) return fail(SGR_EINVAL, "flip mask given without flip_quat");
+	for (int k = 0; k < num_segments; k++) {
+		const SgrSegmentGrads &g = grads[k];
+		if (segments[k].count > 0 && (!g.xyz || !g.rotation || !g.scaling || !g.opacity || !g.features_dc || (M > 1 && !g.features_rest)))
+			return fail(SGR_EINVAL, "segment %d has a NULL gradient array", k);
+	}
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_compose_bwd(segments, grads, num_segments, M, poses, idft, flip, flip_quat, dL_dmeans3D, dL_drotations, dL_dscales,
+	                           dL_dopacities, dL_dshs, pose_scratch, dposes, st),
+	        "compose_bwd");
+	return SGR_OK;
+}
+
 size_t sgr_knn_scratch_bytes(int32_t P) { return knn_scratch_bytes(P); }
 
 int sgr_knn_mean_dist2(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes, void *stream) {

@@ -229,6 +229,11 @@ cudaError_t launch_preprocess_bwd(const FrameDev &f, const float *means3D, const
                                   const int32_t *radii, GeomView g, const float *grad2d, float *dL_dmeans3D,
                                   float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity,
                                   float *dL_dscales, float *dL_drot, float *dL_dcov3D, cudaStream_t st);
+cudaError_t launch_compose_fwd(const SgrSegment *segs, int nseg, int M, const float *poses, const float *idft, const uint8_t *flip,
+                               const float *flip_quat, float *xyz, float *rot, float *scale, float *opac, float *sh, cudaStream_t st);
+cudaError_t launch_compose_bwd(const SgrSegment *segs, const SgrSegmentGrads *grads, int nseg, int M, const float *poses, const float *idft,
+                               const uint8_t *flip, const float *flip_quat, const float *g_xyz, const float *g_rot, const float *g_scale,
+                               const float *g_opac, const float *g_sh, float *acc, float *dposes, cudaStream_t st);
 size_t knn_scratch_bytes(int P);
 cudaError_t launch_knn(int P, const float *points, float *out, void *scratch, size_t scratch_bytes, cudaStream_t st);
 

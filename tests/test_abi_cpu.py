@@ -213,9 +213,10 @@ def test_peer_workspace_layout_is_aligned_and_ordered():
     from street_gaussians_b200.sharded import PeerWorkspace
     st = sgb.GaussianRasterizationSettings(480, 640, 0.5, 0.4, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 3, torch.zeros(3), False, False)
     P_total = 8 * 12_501
-    gb, ib, off_radii, off_grad, total = PeerWorkspace.layout(st, P_total, torch.device("cpu"))
+    gb, ib, off_radii, off_grad, off_flags, total = PeerWorkspace.layout(st, P_total, torch.device("cpu"))
     assert gb >= P_total * 48 and off_radii >= gb and off_radii % 256 == 0
-    assert off_grad >= off_radii + 4 * P_total and off_grad % 256 == 0 and total == off_grad + 48 * P_total and ib > 0
+    assert off_grad >= off_radii + 4 * P_total and off_grad % 256 == 0 and ib > 0
+    assert off_flags >= off_grad + 48 * P_total and off_flags % 256 == 0 and total == off_flags + 256  # barrier pad: 16 x u32, padded
 
 
 def test_peer_workspace_emulation_wires_the_peer_table():
@@ -233,5 +234,7 @@ def test_peer_workspace_emulation_wires_the_peer_table():
         assert ws.radii_all.dtype == torch.int32 and ws.radii_all.shape == (world * chunk,)
         for p in range(world):
             assert ws.peers.records[p] == bases[p] and ws.peers.radii[p] == bases[p] + ws.off_radii
-            assert ws.peers.grad2d[p] == bases[p] + ws.off_grad
+            assert ws.peers.grad2d[p] == bases[p] + ws.off_grad and ws.peers.flags[p] == bases[p] + ws.off_flags
+        assert int(ws.buf[ws.off_flags:].sum()) == 0 and ws.epoch == 0  # barrier pads start at epoch 0
+        assert ws.next_epochs(2) == 2 and ws.next_epochs() == 3
         ws.barrier()  # no symmetric-memory handle in emulation: a no-op
