@@ -50,7 +50,8 @@ def compose(models, poses, idft, flip, flip_quat):
         x_l = torch.where(fm[:, None], m["xyz"] * torch.tensor([1.0, -1.0, 1.0], dtype=m["xyz"].dtype, device=m["xyz"].device), m["xyz"])  # :347-349 (flip_axis = 1)
         xyz.append(torch.einsum("ij,bj->bi", quat_to_matrix(q_obj[None])[0], x_l) + t_obj)                     # :350-351
         r_l = F.normalize(m["rotation"])
-        r_l = torch.where(fm[:, None], quat_mul(flip_quat.to(r_l.dtype).expand(n, 4), r_l), r_l)                  # :319-323
+        if flip is not None:
+            r_l = torch.where(fm[:, None], quat_mul(flip_quat.to(r_l.dtype).expand(n, 4), r_l), r_l)              # :319-323
         rot.append(F.normalize(quat_mul(q_obj.expand(n, 4), r_l)))                                               # :324-325
         dc = (m["features_dc"] * idft[a][None, :, None].to(m["features_dc"].dtype)).sum(1, keepdim=True)        # gaussian_model_actor.py:76-77
         feat.append(torch.cat((dc, m["features_rest"]), 1))

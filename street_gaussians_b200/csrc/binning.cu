@@ -275,11 +275,13 @@ __global__ void count_status_kernel(const uint32_t *__restrict__ offsets, int P,
 	status[2] |= R > cap ? 1u : 0u;  // (bit 1 = Gaussian-capacity overflow of the compacted depth order; the words are zeroed per forward)
 	status[3] = emitted;
 }
+// grid-stride over [emitted, cap): the number of padding slots is only known on the device, and one thread per slot of the whole
+// capacity (the round-1 launch) spent 31 us retiring 55k empty blocks
 template <typename KeyT>
 __global__ void __launch_bounds__(256) pad_keys_kernel(KeyT *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t cap,
                                                       const uint32_t *__restrict__ status) {
-	const uint32_t i = status[3] + blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < cap) {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i = status[3] + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
 		keys[i] = (KeyT)~(KeyT)0;
 		vals[i] = 0u;
 	}
@@ -309,7 +311,7 @@ cudaError_t launch_binning(const FrameDev &f, GeomView g, const int32_t *radii, 
 	const unsigned nblk = (unsigned)((n_order + 255) / 256);
 	const unsigned nbig_blk = 148 * 4;  // persistent-style grid for the deferred large rectangles
 	if ((e = cudaMemsetAsync(g.big_count, 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
-	const unsigned npad_blk = bounded ? (unsigned)((cap + 255) / 256) : 0u;  // upper bound; threads past `cap` exit
+	const unsigned npad_blk = bounded ? (unsigned)(cap / 256 + 1 < 148 * 8 ? cap / 256 + 1 : 148 * 8) : 0u;
 	const int sort_bits = bounded ? (ntile <= 65535 ? 16 : 32) : bits_for(ntile);
 	if (ntile <= 65535 || (!bounded && ntile <= 65536)) {  // 16-bit tile ids (the key arrays are allocated for 32-bit ids either way)
 		uint16_t *kin = reinterpret_cast<uint16_t *>(b.keys_in), *kout = reinterpret_cast<uint16_t *>(b.keys_out);

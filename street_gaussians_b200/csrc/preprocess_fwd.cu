@@ -10,6 +10,8 @@
 // contribution (exact opacity-aware row-span cull, tile_visit.cuh) and that lie in this process's tile-row band,
 // (4) large rectangles are counted warp-cooperatively instead of by one thread, (5) a 32-bit depth key per Gaussian
 // feeds the depth pre-sort of binning.cu.
+#include <cstdlib>
+
 #include "sgr_common.cuh"
 #include "tile_visit.cuh"
 
@@ -104,18 +106,15 @@ __device__ __forceinline__ Projected project_gaussian(const FrameDev &f, int idx
 	return o;
 }
 
-// SH (degree <= 3) -> RGB with +0.5 and clamp-at-zero flags (reference forward.cu:20-71).  sh points at this
-// Gaussian's [M,3] coefficient row in global memory.
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float3 campos, const float *__restrict__ sh, int M,
-                                            uint32_t &clamp_bits) {
-	float3 d = make_float3(p.x - campos.x, p.y - campos.y, p.z - campos.z);
-	const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-	const float x = d.x / len, y = d.y / len, z = d.z / len;
-	float c[48];
-	const int n = min(M, (deg + 1) * (deg + 1)) * 3;
-	// Each thread walks its own 12*M-byte row with 16-B loads; the two halves of every 32-B sector are consumed by
-	// consecutive loads of the same thread, so L1 absorbs the stride.  (Staging the rows through shared memory, as
-	// preprocess_bwd does for its read+write pair, was measured SLOWER here: 264 vs 168 us on config C — profiles/.)
+// SH (degree <= 3) -> RGB with +0.5 and clamp-at-zero flags (reference forward.cu:20-71).  c[] holds this Gaussian's
+// coefficient row (coefficient-major, RGB innermost), loaded by one of the two loaders below.
+constexpr int kShStride = 52;  // floats between the rows of a warp's shared-memory stage: 208 B = 13 x 16 B, so the rows stay
+                               // 16-B aligned for cp.async.bulk / LDS.128 and the 8 lanes of a quarter-warp hit 8 distinct
+                               // 16-B bank groups ((13 l + k) mod 8)
+
+// Each thread walks its own 12*M-byte row in global memory with 16-B loads (the pre-TMA path; still used when the row size is
+// not a multiple of 16 B, i.e. M = 1 or 9).
+__device__ __forceinline__ void load_sh_global(float *c, const float *__restrict__ sh, int M, int n) {
 	if (((M * 3) & 3) == 0) {
 		const float4 *s4 = reinterpret_cast<const float4 *>(sh);
 #pragma unroll
@@ -129,6 +128,22 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float
 		for (int k = 0; k < 48; k++)
 			if (k < n) c[k] = __ldg(sh + k);
 	}
+}
+// The row was brought into shared memory by a TMA bulk copy issued at the top of the kernel (preprocess_fwd_kernel<.., TMA>).
+__device__ __forceinline__ void load_sh_smem(float *c, uint32_t row, int n) {
+#pragma unroll
+	for (int k = 0; k < 12; k++)
+		if (4 * k < n) {
+			float4 v;
+			asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(row + 16u * k));
+			c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+		}
+}
+
+__device__ __forceinline__ float3 sh_eval(int deg, const float3 p, const float3 campos, const float *c, uint32_t &clamp_bits) {
+	float3 d = make_float3(p.x - campos.x, p.y - campos.y, p.z - campos.z);
+	const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+	const float x = d.x / len, y = d.y / len, z = d.z / len;
 	float res[3];
 #pragma unroll
 	for (int ch = 0; ch < 3; ch++) {
@@ -160,7 +175,12 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float3 p, const float
 // SCATTER = true (with COUNT = false): sgr_sharded_forward — the record additionally goes straight from registers into the
 // gathered arrays of exactly the ranks whose cyclic tile-row band its 3-sigma rectangle meets (NVLink peer stores), and the
 // radius (0 = "not yours") to every rank; threads f.P .. pt.chunk-1 are the padding slots of this rank's chunk.
-template <bool COUNT, bool SCATTER = false>
+// TMA = true: the warp's 32 SH rows (12*M bytes each, contiguous in `shs`) are fetched by cp.async.bulk into shared memory at the
+// very top of the kernel — before the position is even loaded — and consumed after the projection math, so the one large read
+// of this kernel (192 of ~250 B per Gaussian at SH degree 3) is in flight during all of it instead of being 12 dependent
+// per-thread loads issued after the cull.  One mbarrier per warp, single phase.  (Rows of Gaussians that turn out culled are
+// fetched too: ~20 % of the rows on the BASELINE frames, paid for by the overlap.)
+template <bool COUNT, bool SCATTER = false, bool TMA = false>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, const PeerTable pt, const float *__restrict__ means3D,
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,
                                                              const float *__restrict__ opacities, const float *__restrict__ scales,
@@ -168,8 +188,30 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
                                                              int32_t *__restrict__ radii, GaussRec *__restrict__ rec,
                                                              uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ depth_key,
                                                              uint32_t *__restrict__ iota) {
+	extern __shared__ __align__(16) unsigned char s_stage[];  // TMA: [8 warps][32 rows][kShStride floats] + 8 mbarriers
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = idx < f.P;
+	uint32_t sh_row = 0, sh_bar = 0;
+	bool sh_pending = false;  // this warp has bulk copies in flight: every lane must pass the barrier before it exits
+	if (TMA) {
+		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+		const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_stage);
+		sh_row = sbase + (uint32_t)((warp * 32 + lane) * kShStride) * 4u;
+		sh_bar = sbase + (uint32_t)(8 * 32 * kShStride) * 4u + (uint32_t)warp * 8u;
+		const int first = blockIdx.x * blockDim.x + warp * 32;
+		const int rows = min(32, f.P - first);
+		sh_pending = rows > 0;
+		if (sh_pending) {
+			const uint32_t row_bytes = (uint32_t)f.M * 12u;
+			if (lane == 0) {
+				mbar_init(sh_bar, 1);
+				fence_proxy_async();
+			}
+			__syncwarp();
+			if (in_range) bulk_g2s(sh_row, shs + (size_t)idx * f.M * 3, row_bytes, sh_bar);
+			if (lane == 0) mbar_expect_tx(sh_bar, row_bytes * (uint32_t)rows);
+		}
+	}
 	Projected pr;
 	pr.ok = false;
 	pr.radius = 0;
@@ -179,13 +221,18 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
 		pr = project_gaussian(f, idx, p, scales, rotations, cov3D_precomp);
 	}
+	if (TMA && sh_pending) mbar_wait(sh_bar, 0);  // all rows of the warp have landed (also keeps the CTA alive until they have)
 	if (in_range) {
 		if (pr.ok) {
 			float3 rgb;
 			uint32_t clamp_bits = 0;
 			if (colors_precomp == nullptr) {
 				const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
-				rgb = sh_to_rgb(f.D, p, campos, shs + (size_t)idx * f.M * 3, f.M, clamp_bits);
+				float c[48];
+				const int n = min(f.M, (f.D + 1) * (f.D + 1)) * 3;
+				if (TMA) load_sh_smem(c, sh_row, n);
+				else load_sh_global(c, shs + (size_t)idx * f.M * 3, f.M, n);
+				rgb = sh_eval(f.D, p, campos, c, clamp_bits);
 			} else {
 				rgb = make_float3(colors_precomp[3 * (size_t)idx], colors_precomp[3 * (size_t)idx + 1], colors_precomp[3 * (size_t)idx + 2]);
 			}
@@ -247,13 +294,30 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *_
 	present[idx] = pv.z > 0.2f ? 1 : 0;
 }
 
+// TMA staging applies when the rows are 16-B multiples (M = 4, 8, 12, 16: SH degree 1 and 3) and 16-B aligned
+static bool sh_rows_fit_tma(const FrameDev &f, const float *shs) {
+	static const bool disabled = getenv("SGR_NO_TMA") != nullptr;  // A/B switch for profiling: per-thread global loads instead
+	if (disabled) return false;
+	return shs != nullptr && f.M > 0 && f.M <= 16 && (f.M * 12) % 16 == 0 && (reinterpret_cast<uintptr_t>(shs) & 15u) == 0;
+}
+constexpr size_t kFwdStageBytes = (size_t)8 * 32 * kShStride * sizeof(float) + 8 * sizeof(uint64_t);  // 53,312 B
+
 cudaError_t launch_preprocess_fwd(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
                                   const float *opacities, const float *scales, const float *rotations,
                                   const float *cov3D_precomp, int32_t *radii, GeomView g, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
 	count_launch();
-	preprocess_fwd_kernel<true><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities, scales, rotations,
-	                                                                  cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
+	if (sh_rows_fit_tma(f, shs)) {
+		static std::atomic<uint64_t> configured{0};
+		cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<true, false, true>, (int)kFwdStageBytes, configured);
+		if (e != cudaSuccess) return e;
+		preprocess_fwd_kernel<true, false, true><<<(f.P + 255) / 256, 256, kFwdStageBytes, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities,
+		                                                                                       scales, rotations, cov3D_precomp, radii, g.rec,
+		                                                                                       g.tiles_touched, g.depth_key, g.iota);
+	} else {
+		preprocess_fwd_kernel<true><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities, scales, rotations,
+		                                                                  cov3D_precomp, radii, g.rec, g.tiles_touched, g.depth_key, g.iota);
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_project(const FrameDev &f, const float *means3D, const float *shs, const float *colors_precomp,
@@ -261,8 +325,17 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
                            int32_t *radii, GaussRec *rec, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
 	count_launch();
-	preprocess_fwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities, scales, rotations,
-	                                                                   cov3D_precomp, radii, rec, nullptr, nullptr, nullptr);
+	if (sh_rows_fit_tma(f, shs)) {
+		static std::atomic<uint64_t> configured{0};
+		cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<false, false, true>, (int)kFwdStageBytes, configured);
+		if (e != cudaSuccess) return e;
+		preprocess_fwd_kernel<false, false, true><<<(f.P + 255) / 256, 256, kFwdStageBytes, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities,
+		                                                                                        scales, rotations, cov3D_precomp, radii, rec, nullptr,
+		                                                                                        nullptr, nullptr);
+	} else {
+		preprocess_fwd_kernel<false><<<(f.P + 255) / 256, 256, 0, st>>>(f, PeerTable{}, means3D, shs, colors_precomp, opacities, scales, rotations,
+		                                                                   cov3D_precomp, radii, rec, nullptr, nullptr, nullptr);
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_project_scatter(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
@@ -270,9 +343,17 @@ cudaError_t launch_project_scatter(const FrameDev &f, const PeerTable &pt, const
                                    const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, cudaStream_t st) {
 	if (pt.chunk == 0) return cudaSuccess;
 	count_launch();
-	preprocess_fwd_kernel<false, true><<<(unsigned)((pt.chunk + 255) / 256), 256, 0, st>>>(f, pt, means3D, shs, colors_precomp, opacities, scales,
-	                                                                                       rotations, cov3D_precomp, radii_local, rec_local,
-	                                                                                       nullptr, nullptr, nullptr);
+	const unsigned nblk = (unsigned)((pt.chunk + 255) / 256);
+	if (sh_rows_fit_tma(f, shs)) {
+		static std::atomic<uint64_t> configured{0};
+		cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<false, true, true>, (int)kFwdStageBytes, configured);
+		if (e != cudaSuccess) return e;
+		preprocess_fwd_kernel<false, true, true><<<nblk, 256, kFwdStageBytes, st>>>(f, pt, means3D, shs, colors_precomp, opacities, scales, rotations,
+		                                                                          cov3D_precomp, radii_local, rec_local, nullptr, nullptr, nullptr);
+	} else {
+		preprocess_fwd_kernel<false, true><<<nblk, 256, 0, st>>>(f, pt, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+		                                                         radii_local, rec_local, nullptr, nullptr, nullptr);
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,

@@ -79,14 +79,18 @@ def _field(gen, n, tanx, tany, zmin=2.0, zmax=80.0, near_frac=0.02, scale_med=0.
 
 def make_scene(P: int, width: int, height: int, sh_degree: int = 3, seed: int = 0, n_vehicles: int = 0,
                per_vehicle: int = 0, semantics: int = 0, pose: bool = False, fovx_deg: float = 50.0,
-               bg=(0.0, 0.0, 0.0), scale_med: float = 0.007) -> Dict:
+               bg=(0.0, 0.0, 0.0), scale_med: float = 0.007, with_raw: bool = False) -> Dict:
     """P background Gaussians (+ n_vehicles x per_vehicle posed 'vehicle' clusters, composed the way
-    lib/models/street_gaussian_model.py:335-363 does: x_world = R_obj x_local + t_obj, q_world = q_obj * q_local)."""
+    lib/models/street_gaussian_model.py:335-363 does: x_world = R_obj x_local + t_obj, q_world = q_obj * q_local).
+    with_raw: also return out["raw"] = dict(models=[background, vehicle_0, ...] of RAW parameters (local frame, log scale, logit
+    opacity, features_dc / features_rest split; the layout street_gaussians_b200.compose consumes), poses [n_vehicles, 7], idft
+    [n_vehicles, 1]) whose composition reproduces the composed arrays above up to fp32 rounding."""
     gen = torch.Generator().manual_seed(seed)
     w2c = random_pose(gen) if pose else None
     cam = make_camera(width, height, fovx_deg, w2c, sh_degree, bg)
     tanx, tany = cam["tanfovx"], cam["tanfovy"]
     means, scales, rot, opac = _field(gen, P, tanx, tany, scale_med=scale_med)
+    raw_local, raw_pose = [], []
     if n_vehicles and per_vehicle:
         ms, ss, rs, os_ = [means], [scales], [rot], [opac]
         for v in range(n_vehicles):
@@ -101,6 +105,8 @@ def make_scene(P: int, width: int, height: int, sh_degree: int = 3, seed: int = 
             m = local @ Rm.t() + torch.tensor([cx, cy, depth])
             s = torch.exp(torch.randn(per_vehicle, 3, generator=gen) * 0.5 + math.log(0.03)).clamp(1e-3, 0.5)
             q = torch.randn(per_vehicle, 4, generator=gen)
+            raw_local.append((local, q.clone()))
+            raw_pose.append(torch.cat([q_obj, torch.tensor([cx, cy, depth])]))
             q = _quat_mul(q_obj.expand_as(q), q / q.norm(dim=-1, keepdim=True))
             q = q / q.norm(dim=-1, keepdim=True)
             o = torch.sigmoid(torch.randn(per_vehicle, 1, generator=gen) * 2.0 + 1.0)
@@ -115,6 +121,19 @@ def make_scene(P: int, width: int, height: int, sh_degree: int = 3, seed: int = 
     shs[:, 0, :] = torch.randn(n, 3, generator=gen)
     out = dict(cam=cam, means3D=means.float().contiguous(), scales=scales.float().contiguous(),
                rotations=rot.float().contiguous(), opacities=opac.float().contiguous(), shs=shs.float().contiguous())
+    if with_raw:
+        if w2c is not None:
+            raise ValueError("with_raw needs pose=False (the raw actor frames are expressed in the identity-camera world)")
+        bounds = [0, P] + [P + (v + 1) * per_vehicle for v in range(len(raw_local))]
+        models = []
+        for k in range(len(bounds) - 1):
+            lo, hi = bounds[k], bounds[k + 1]
+            xyz_k, rot_k = (means[lo:hi], rot[lo:hi]) if k == 0 else raw_local[k - 1]
+            models.append(dict(xyz=xyz_k.float().contiguous(), rotation=rot_k.float().contiguous(), scaling=torch.log(scales[lo:hi]).float().contiguous(),
+                               opacity=torch.logit(opac[lo:hi].double().clamp(1e-7, 1 - 1e-7)).float().contiguous(),
+                               features_dc=shs[lo:hi, 0:1].float().contiguous(), features_rest=shs[lo:hi, 1:].float().contiguous()))
+        out["raw"] = dict(models=models, poses=torch.stack(raw_pose).float() if raw_pose else torch.zeros(0, 7),
+                          idft=torch.ones(len(raw_pose), 1))
     if semantics:
         out["semantics"] = torch.rand(n, semantics, generator=gen).float().contiguous()
     npx = width * height
