@@ -282,6 +282,47 @@ int sgr_compose_backward(const SgrSegment *segments, const SgrSegmentGrads *grad
                          const float *dL_drotations, const float *dL_dscales, const float *dL_dopacities, const float *dL_dshs,
                          float *dposes, float *pose_scratch, void *stream);
 
+/* ---- Image-space losses with their gradient ----
+ * value = w_l1 * L1(image, gt, mask) + w_ssim * SSIM(image, gt, mask)  and  dL_dimage = d value / d image  in two kernels.
+ * Replaces l1_loss (lib/utils/loss_utils.py:21-37), ssim / _ssim (:91-126: 11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2,
+ * C2 = 0.03^2, both images zeroed outside the mask, mean over ALL pixels) and the autograd replay of both.  The training loss of
+ * train.py:103-104 is  w_l1 = (1 - lambda_dssim) * lambda_l1,  w_ssim = -lambda_dssim,  plus the constant lambda_dssim.
+ *   image, gt: [C,H,W] device; mask: uint8 [H*W] device or NULL; dL_dimage: [C,H,W] device or NULL (value only).
+ *   scalars (device, 4 floats): {value, L1, SSIM, number of masked pixels}.  scratch: sgr_image_loss_scratch_bytes(C,H,W) bytes. */
+size_t sgr_image_loss_scratch_bytes(int32_t C, int32_t H, int32_t W);
+int sgr_image_loss(int32_t C, int32_t H, int32_t W, const float *image, const float *gt, const uint8_t *mask, float w_l1, float w_ssim,
+                   float *dL_dimage, float *scalars, void *scratch, size_t scratch_bytes, void *stream);
+/* Sky / accumulation loss (train.py:107-113): acc clamped to [1e-6, 1-1e-6], mean over the N pixels of sky ? -log(1-acc) : -log(acc).
+ * scalars (device, 2 floats): {weight * mean, mean}; dL_dacc[N] (or NULL) = weight * d mean / d acc.  scratch: >= 8 bytes. */
+int sgr_sky_loss(int64_t N, const float *acc, const uint8_t *sky_mask, float weight, float *dL_dacc, float *scalars, void *scratch,
+                 void *stream);
+
+/* ---- Post-backward bookkeeping of a training iteration ----
+ * Densification statistics of StreetGaussianModel.set_max_radii2D + add_densification_stats
+ * (lib/models/street_gaussian_model.py:551-571), all sub-models in one pass over the composed index space: for every Gaussian
+ * with radii > 0:  max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum[:,0] += |grad.xy|;  [:,1] += |grad.z|;  denom += 1.
+ * segments: HOST array, ascending and gap-free like SgrSegment; radii[P] int32 and means2D_grad[P,3] (viewspace_points.grad) device. */
+typedef struct SgrStatSegment {
+	int32_t start, count;
+	float *max_radii2D;         /* [count]    */
+	float *xyz_gradient_accum;  /* [count,2]  */
+	float *denom;               /* [count,1]  */
+} SgrStatSegment;
+int sgr_densify_stats(const SgrStatSegment *segments, int32_t num_segments, const int32_t *radii, const float *means2D_grad, void *stream);
+/* One multi-tensor Adam step (GaussianModel.update_optimizer -> torch.optim.Adam.step, lib/models/gaussian_model.py:300-303, 316-318:
+ * no weight decay, no amsgrad): for each tensor  m <- m + (g - m)(1 - beta1);  v <- beta2 v + (1 - beta2) g^2;
+ * param <- param - lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).  `step` is the 1-based step count AFTER
+ * this update (torch increments before use).  tensors: HOST array; every pointer device, fp32, `numel` elements. */
+typedef struct SgrAdamTensor {
+	float *param;
+	const float *grad;
+	float *exp_avg, *exp_avg_sq;
+	int64_t numel;
+	float lr;
+	int32_t step;
+} SgrAdamTensor;
+int sgr_adam_step(const SgrAdamTensor *tensors, int32_t num_tensors, float beta1, float beta2, float eps, void *stream);
+
 /* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
  * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */
 int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,

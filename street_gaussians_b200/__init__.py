@@ -14,6 +14,7 @@ from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, Inst
                          distCUDA2, rasterize_gaussians)
 
 from .composer import compose  # noqa: E402,F401
+from . import losses, training  # noqa: E402,F401
 
 __all__ = ["compose", "GaussianRasterizationSettings", "GaussianRasterizer", "TileRowBand", "InstanceCapacity", "rasterize_gaussians", "distCUDA2",
            "install_shims"]

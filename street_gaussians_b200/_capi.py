@@ -15,7 +15,8 @@ SYMBOLS = ["sgr_abi_version", "sgr_last_error", "sgr_launch_count", "sgr_state_s
            "sgr_backward_geom", "sgr_backward", "sgr_mark_visible", "sgr_visible_filter", "sgr_knn_scratch_bytes",
            "sgr_knn_mean_dist2", "sgr_record_bytes", "sgr_project", "sgr_forward_records",
            "sgr_scatter_records", "sgr_gather_grad2d", "sgr_peer_barrier", "sgr_sharded_forward", "sgr_sharded_backward",
-           "sgr_compose_forward", "sgr_compose_backward"]
+           "sgr_compose_forward", "sgr_compose_backward", "sgr_image_loss_scratch_bytes", "sgr_image_loss", "sgr_sky_loss",
+           "sgr_densify_stats", "sgr_adam_step"]
 
 
 class SgrFrame(C.Structure):
@@ -45,6 +46,15 @@ class SgrSegment(C.Structure):
 class SgrSegmentGrads(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("rotation", C.c_void_p), ("scaling", C.c_void_p), ("opacity", C.c_void_p), ("features_dc", C.c_void_p),
                 ("features_rest", C.c_void_p)]
+
+
+class SgrStatSegment(C.Structure):
+    _fields_ = [("start", C.c_int32), ("count", C.c_int32), ("max_radii2D", C.c_void_p), ("xyz_gradient_accum", C.c_void_p), ("denom", C.c_void_p)]
+
+
+class SgrAdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("numel", C.c_int64),
+                ("lr", C.c_float), ("step", C.c_int32)]
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -112,6 +122,16 @@ def lib():
     L.sgr_compose_forward.argtypes = [C.POINTER(SgrSegment), C.c_int32, C.c_int32] + [vp] * 10
     L.sgr_compose_backward.restype = C.c_int
     L.sgr_compose_backward.argtypes = [C.POINTER(SgrSegment), C.POINTER(SgrSegmentGrads), C.c_int32, C.c_int32] + [vp] * 12
+    L.sgr_image_loss_scratch_bytes.restype = C.c_size_t
+    L.sgr_image_loss_scratch_bytes.argtypes = [C.c_int32] * 3
+    L.sgr_image_loss.restype = C.c_int
+    L.sgr_image_loss.argtypes = [C.c_int32] * 3 + [vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, C.c_size_t, vp]
+    L.sgr_sky_loss.restype = C.c_int
+    L.sgr_sky_loss.argtypes = [C.c_int64, vp, vp, C.c_float, vp, vp, vp, vp]
+    L.sgr_densify_stats.restype = C.c_int
+    L.sgr_densify_stats.argtypes = [C.POINTER(SgrStatSegment), C.c_int32, vp, vp, vp]
+    L.sgr_adam_step.restype = C.c_int
+    L.sgr_adam_step.argtypes = [C.POINTER(SgrAdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, vp]
     L.sgr_backward_blend.restype = C.c_int
     L.sgr_backward_blend.argtypes = [C.POINTER(SgrFrame), C.c_int64] + [vp] * 12
     L.sgr_backward_geom.restype = C.c_int

@@ -633,6 +633,60 @@ int sgr_compose_backward(const SgrSegment *segments, const SgrSegmentGrads *grad
 	return SGR_OK;
 }
 
+size_t sgr_image_loss_scratch_bytes(int32_t C, int32_t H, int32_t W) { return (C > 0 && H > 0 && W > 0) ? image_loss_scratch_bytes(C, H, W) : 0; }
+
+int sgr_image_loss(int32_t C, int32_t H, int32_t W, const float *image, const float *gt, const uint8_t *mask, float w_l1, float w_ssim,
+                   float *dL_dimage, float *scalars, void *scratch, size_t scratch_bytes, void *stream) {
+	if (C <= 0 || H <= 0 || W <= 0) return fail(SGR_EINVAL, "bad image size C=%d H=%d W=%d", C, H, W);
+	if (!image || !gt || !scalars) return fail(SGR_EINVAL, "NULL pointer passed to sgr_image_loss");
+	if (!scratch || scratch_bytes < image_loss_scratch_bytes(C, H, W))
+		return fail(SGR_ENOMEM, "image loss scratch too small: %zu < %zu", scratch_bytes, image_loss_scratch_bytes(C, H, W));
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_image_loss(C, H, W, image, gt, mask, w_l1, w_ssim, dL_dimage, scalars, scratch, st), "image_loss");
+	return SGR_OK;
+}
+
+int sgr_sky_loss(int64_t N, const float *acc, const uint8_t *sky_mask, float weight, float *dL_dacc, float *scalars, void *scratch, void *stream) {
+	if (N <= 0) return fail(SGR_EINVAL, "N must be positive");
+	if (!acc || !sky_mask || !scalars || !scratch) return fail(SGR_EINVAL, "NULL pointer passed to sgr_sky_loss");
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_sky_loss((size_t)N, acc, sky_mask, weight, dL_dacc, scalars, scratch, st), "sky_loss");
+	return SGR_OK;
+}
+
+int sgr_densify_stats(const SgrStatSegment *segments, int32_t num_segments, const int32_t *radii, const float *means2D_grad, void *stream) {
+	if (!segments || num_segments <= 0) return fail(SGR_EINVAL, "segment table is empty");
+	int64_t at = 0;
+	for (int k = 0; k < num_segments; k++) {
+		const SgrStatSegment &s = segments[k];
+		if (s.start != at || s.count < 0) return fail(SGR_EINVAL, "segment %d: start %d (expected %lld), count %d", k, s.start, (long long)at, s.count);
+		if (s.count > 0 && (!s.max_radii2D || !s.xyz_gradient_accum || !s.denom)) return fail(SGR_EINVAL, "segment %d has a NULL statistics array", k);
+		at += s.count;
+	}
+	if (at == 0) return SGR_OK;
+	if (!radii || !means2D_grad) return fail(SGR_EINVAL, "NULL pointer passed to sgr_densify_stats");
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_densify_stats(segments, num_segments, radii, means2D_grad, st), "densify_stats");
+	return SGR_OK;
+}
+
+int sgr_adam_step(const SgrAdamTensor *tensors, int32_t num_tensors, float beta1, float beta2, float eps, void *stream) {
+	if (num_tensors < 0 || (num_tensors > 0 && !tensors)) return fail(SGR_EINVAL, "bad tensor table");
+	for (int k = 0; k < num_tensors; k++) {
+		const SgrAdamTensor &a = tensors[k];
+		if (a.numel < 0 || a.step < 1) return fail(SGR_EINVAL, "tensor %d: numel %lld, step %d (step counts from 1)", k, (long long)a.numel, a.step);
+		if (a.numel > 0 && (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq)) return fail(SGR_EINVAL, "tensor %d has a NULL pointer", k);
+	}
+	if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f)) return fail(SGR_EINVAL, "betas must lie in [0, 1)");
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	const bool debug = false;
+	SGR_TRY(launch_adam(tensors, num_tensors, beta1, beta2, eps, st), "adam");
+	return SGR_OK;
+}
+
 size_t sgr_knn_scratch_bytes(int32_t P) { return knn_scratch_bytes(P); }
 
 int sgr_knn_mean_dist2(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes, void *stream) {

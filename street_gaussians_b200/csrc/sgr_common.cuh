@@ -269,6 +269,12 @@ cudaError_t launch_compose_fwd(const SgrSegment *segs, int nseg, int M, const fl
 cudaError_t launch_compose_bwd(const SgrSegment *segs, const SgrSegmentGrads *grads, int nseg, int M, const float *poses, const float *idft,
                                const uint8_t *flip, const float *flip_quat, const float *g_xyz, const float *g_rot, const float *g_scale,
                                const float *g_opac, const float *g_sh, float *acc, float *dposes, cudaStream_t st);
+size_t image_loss_scratch_bytes(int C, int H, int W);
+cudaError_t launch_image_loss(int C, int H, int W, const float *img, const float *gt, const uint8_t *mask, float w_l1, float w_ssim, float *grad,
+                              float *scalars, void *scratch, cudaStream_t st);
+cudaError_t launch_sky_loss(size_t N, const float *accm, const uint8_t *sky, float weight, float *grad, float *scalars, void *scratch, cudaStream_t st);
+cudaError_t launch_densify_stats(const SgrStatSegment *segs, int nseg, const int32_t *radii, const float *grad2d, cudaStream_t st);
+cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, float beta1, float beta2, float eps, cudaStream_t st);
 size_t knn_scratch_bytes(int P);
 cudaError_t launch_knn(int P, const float *points, float *out, void *scratch, size_t scratch_bytes, cudaStream_t st);
 
