@@ -14,28 +14,24 @@
 //            the 8 chunk-threads of a splat combine with a 3-step butterfly, and 11 global atomics per (tile, splat) leave
 //            the SM — exactly one per component, as in blend_bwd.cu.
 // No per-pair shuffles, selects or shared-memory partial slabs.  Same math as blend_bwd.cu up to summation order.
-#include <cstdlib>
-
+//
+// Measured and removed in round 2 (B200, config C; profiles/r02_summary.md): ONE barrier per batch with a double-buffered (w, q)
+// matrix and triple-buffered records, so that phase 2 of batch b overlaps phase 1 of batch b+1.  The shared-memory budget forces
+// 16-splat batches (2 x 32 KB), i.e. 16 phase-2 threads per splat, a 4-step butterfly and twice the per-splat fixed cost:
+// 677 us vs 618 us for this kernel; 8-splat batches (4 CTAs/SM) 775 us; 32-splat double-buffered (1 CTA/SM) 1138 us.
 #include "sgr_common.cuh"
 
 namespace sgr {
 
-// Batch size = splats per (w, q) buffer.  Two buffers alternate, so phase 2 of batch b (other warps) overlaps phase 1 of batch
-// b + 1 (this warp) and ONE __syncthreads per batch suffices — the round-1 kernel used a single [32][256] buffer with two
-// barriers per batch, which serialised the two phases (ncu: 76 % issue-active vs 91 % in the forward kernel).
-// kB2 = splats per (w, q) buffer is a template parameter (8, 16 or 32; 16 by default, SGR_BWD2_BATCH overrides it for profiling):
-// smaller batches cost more barriers per splat but leave room for more CTAs per SM.
+constexpr int kB2 = 32;  // splats per batch
 constexpr uint32_t kRec2 = 48;
-template <int kB2>
-struct Bwd2Layout {
-	static constexpr uint32_t wq = 0;                              // float2 [2][kB2][256]
-	static constexpr uint32_t pix = 2 * kB2 * 256 * 8;             // float4 [256]   dL/dpixel rgb, dL/dpixel depth
-	static constexpr uint32_t pxy = pix + 256 * 16;                // float2 [256]   pixel centre
-	static constexpr uint32_t rec = pxy + 256 * 8;                 // [3][kB2 * 48]  staged GaussRec (triple-buffered, see the loop)
-	static constexpr uint32_t id = rec + 3 * kB2 * kRec2;          // u32 [3][kB2]
-	static constexpr uint32_t mask = id + 3 * kB2 * 4;             // u32 [2][8]     per-warp "slot has contributions" bits
-	static constexpr uint32_t total = mask + 2 * 8 * 4;
-};
+constexpr uint32_t kOffWQ = 0;                            // float2 [kB2][256]
+constexpr uint32_t kOffPix = kB2 * 256 * 8;               // float4 [256]   dL/dpixel rgb, dL/dpixel depth
+constexpr uint32_t kOffPxy = kOffPix + 256 * 16;          // float2 [256]   pixel centre
+constexpr uint32_t kOffRec = kOffPxy + 256 * 8;           // [2][kB2 * 48]  staged GaussRec
+constexpr uint32_t kOffId = kOffRec + 2 * kB2 * kRec2;    // u32 [2][kB2]
+constexpr uint32_t kOffMask = kOffId + 2 * kB2 * 4;       // u32 [8]        per-warp "slot has contributions" bits
+constexpr uint32_t kSmem2 = kOffMask + 8 * 4;
 
 __device__ __forceinline__ float4 ld4(uint32_t a) {
 	float4 v;
@@ -58,18 +54,13 @@ __device__ __forceinline__ void st4(uint32_t a, float4 v) {
 __device__ __forceinline__ void st2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
 __device__ __forceinline__ void stu(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-template <int kB2>
-__global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
+__global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
                                                          const uint32_t *__restrict__ point_list, const GaussRec *__restrict__ rec,
                                                          const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tile_max_contrib,
                                                          const float *__restrict__ alphas, const float *__restrict__ dL_dpixels,
                                                          const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dalphas,
                                                          float *__restrict__ grad2d) {
 	extern __shared__ __align__(16) unsigned char smem2[];
-	static_assert(kB2 == 8 || kB2 == 16 || kB2 == 32, "batch must be 8, 16 or 32");
-	constexpr int kT2 = 256 / kB2;  // phase-2 threads per splat; each walks kB2 pixels
-	using L = Bwd2Layout<kB2>;
-	constexpr uint32_t kOffWQ = L::wq, kOffPix = L::pix, kOffPxy = L::pxy, kOffRec = L::rec, kOffId = L::id, kOffMask = L::mask;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int tile_x = blockIdx.x, tile_y = f.band.begin + blockIdx.y * f.band.step;
 	const int tile = tile_y * f.gx + tile_x;
@@ -104,7 +95,7 @@ __global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(con
 	st4(sb + kOffPix + (uint32_t)tid * 16u, make_float4(dL_dpixel[0], dL_dpixel[1], dL_dpixel[2], dL_dpixel_depth));
 	st2(sb + kOffPxy + (uint32_t)tid * 8u, pixf.x, pixf.y);
 
-	// staging: 4 threads per record (q0, q1, q2, id); slot j of batch b <-> list index (n_eff - b*kB2) - 1 - j
+	// staging: 4 threads per record (q0, q1, q2, id), threads 0..127; slot j of batch b <-> list index (n_eff - b*B) - 1 - j
 	const int ld_slot = tid >> 2, ld_part = tid & 3;
 	float4 rq = make_float4(0, 0, 0, 0);
 	uint32_t rid = 0;
@@ -115,36 +106,30 @@ __global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(con
 			if (ld_part < 3) rq = reinterpret_cast<const float4 *>(rec + rid)[ld_part];
 		}
 	};
-	auto stash = [&](int b) {
-		const uint32_t buf = (uint32_t)(b % 3);
+	auto stash = [&](int buf) {
 		if (ld_slot < kB2) {
-			if (ld_part < 3) st4(sb + kOffRec + buf * (kB2 * kRec2) + (uint32_t)ld_slot * kRec2 + (uint32_t)ld_part * 16u, rq);
-			else stu(sb + kOffId + (buf * kB2 + (uint32_t)ld_slot) * 4u, rid);
+			if (ld_part < 3) st4(sb + kOffRec + (uint32_t)buf * (kB2 * kRec2) + (uint32_t)ld_slot * kRec2 + (uint32_t)ld_part * 16u, rq);
+			else stu(sb + kOffId + (uint32_t)(buf * kB2 + ld_slot) * 4u, rid);
 		}
 	};
 	fetch(0);
 	stash(0);
-	if (nb > 1) fetch(1);
-	__syncthreads();  // record buffer 0 and the per-pixel arrays are published
 
-	// phase-2 role of this thread: kT2 consecutive lanes share a splat, each owns kB2 of the tile's 256 pixels
-	const int p2_slot = tid / kT2, p2_chunk = tid % kT2;
+	// phase-2 role of this thread
+	const int p2_slot = tid >> 3, p2_chunk = tid & 7;
 
-	// Per thread the order is  P1(0) S P2(0) P1(1) S P2(1) ...  with ONE barrier S per batch.  Hazards:
-	//   wq / mask buffer b&1: written in P1(b), read in P2(b); P1(b+2) reuses it, and any thread in P1(b+2) has passed S(b+1), which
-	//     every thread reaches only after its P2(b).
-	//   record buffer b%3: written by stash(b) before S(b-1), read in P1(b) and P2(b); stash(b+3) runs before S(b+2), after S(b+1),
-	//     which every thread reaches only after its P2(b).  (With two record buffers stash(b+2) would race with P2(b) of slow warps.)
 	for (int b = 0; b < nb; b++) {
-		const uint32_t wbuf = (uint32_t)(b & 1);
+		__syncthreads();  // record buffer b&1 published; phase 2 of the previous batch is done with s_wq / s_mask
+		if (b + 1 < nb) fetch(b + 1);
+		const int buf = b & 1;
 		const int hi = n_eff - b * kB2;  // list position (1-based) of slot 0
 		const int cnt = min(kB2, hi);
-		const uint32_t rbase = sb + kOffRec + (uint32_t)(b % 3) * (kB2 * kRec2);
+		const uint32_t rbase = sb + kOffRec + (uint32_t)buf * (kB2 * kRec2);
 
 		// ---------------- phase 1: per-pixel recurrences -> (w, q) ----------------
 		uint32_t wmask = 0u;
 		uint32_t a = rbase;
-		uint32_t wq_addr = sb + kOffWQ + wbuf * (uint32_t)(kB2 * 256 * 8) + (uint32_t)tid * 8u;
+		uint32_t wq_addr = sb + kOffWQ + (uint32_t)tid * 8u;
 		for (int j = 0; j < cnt; j++, a += kRec2, wq_addr += 256u * 8u) {
 			const int contributor = hi - 1 - j;
 			bool valid = contributor < last_contributor;
@@ -189,27 +174,23 @@ __global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(con
 				wmask |= 1u << j;
 			}
 		}
-		if (lane == 0) stu(sb + kOffMask + (wbuf * 8u + (uint32_t)warp) * 4u, wmask);
-		if (b + 1 < nb) stash(b + 1);
-		__syncthreads();  // S(b): wq / mask buffer b&1 and record buffer (b+1)%3 are published
-		if (b + 2 < nb) fetch(b + 2);
+		if (lane == 0) stu(sb + kOffMask + (uint32_t)warp * 4u, wmask);
+		__syncthreads();
 
 		// ---------------- phase 2: per-splat sums over the tile's pixels ----------------
 		{
 			float Sq = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sabs = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
-			// pixel p belongs to warp p / 32 of phase 1; this thread's kB2 pixels sit in ONE such warp when kB2 <= 32
-			const int src_warp = (p2_chunk * kB2) >> 5;
-			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (wbuf * 8u + (uint32_t)src_warp) * 4u) >> p2_slot) & 1u);
+			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (uint32_t)p2_chunk * 4u) >> p2_slot) & 1u);
 			float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
 			if (live) {
 				r0 = ld4(rbase + (uint32_t)p2_slot * kRec2);
 				r1 = ld4(rbase + (uint32_t)p2_slot * kRec2 + 16);
-				const uint32_t row = sb + kOffWQ + wbuf * (uint32_t)(kB2 * 256 * 8) + (uint32_t)(p2_slot * 256 + p2_chunk * kB2) * 8u;
-				const uint32_t pixb = sb + kOffPix + (uint32_t)(p2_chunk * kB2) * 16u;
-				const uint32_t pxyb = sb + kOffPxy + (uint32_t)(p2_chunk * kB2) * 8u;
+				const uint32_t row = sb + kOffWQ + (uint32_t)(p2_slot * 256 + p2_chunk * 32) * 8u;
+				const uint32_t pixb = sb + kOffPix + (uint32_t)(p2_chunk * 32) * 16u;
+				const uint32_t pxyb = sb + kOffPxy + (uint32_t)(p2_chunk * 32) * 8u;
 #pragma unroll 4
-				for (int i = 0; i < kB2; i++) {
-					const uint32_t l = (uint32_t)(i + lane) & (uint32_t)(kB2 - 1);  // bank rotation across the lanes of a warp
+				for (int i = 0; i < 32; i++) {
+					const uint32_t l = (uint32_t)(i + lane) & 31u;  // bank rotation: the 32 lanes of a warp hit 32 distinct pixels
 					const float2 wq = ld2(row + l * 8u);
 					const float4 pg = ld4(pixb + l * 16u);
 					const float2 pc = ld2(pxyb + l * 8u);
@@ -228,11 +209,11 @@ __global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(con
 					Cd += wq.x * pg.w;
 				}
 			}
-			// combine the kT2 threads of each splat (consecutive lanes; kT2 <= 32) — all lanes take part
+			// combine the 8 chunk-threads of each splat (consecutive lanes) — all lanes take part
 			const unsigned any_live = __ballot_sync(0xffffffffu, live);
 			if (any_live) {
 #pragma unroll
-				for (int o = 1; o < kT2; o <<= 1) {
+				for (int o = 1; o < 8; o <<= 1) {
 					Sq += __shfl_xor_sync(0xffffffffu, Sq, o); Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
 					Sy += __shfl_xor_sync(0xffffffffu, Sy, o); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
 					Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o); Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
@@ -240,15 +221,14 @@ __global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(con
 					Cg += __shfl_xor_sync(0xffffffffu, Cg, o); Cb += __shfl_xor_sync(0xffffffffu, Cb, o);
 					Cd += __shfl_xor_sync(0xffffffffu, Cd, o);
 				}
-				// is any thread of this splat live?  (bits of the kT2 lanes of this slot in the ballot)
-				const int g0 = lane & ~(kT2 - 1);
-				const unsigned grp = (kT2 == 32) ? any_live : ((any_live >> g0) & ((1u << (kT2 & 31)) - 1u));
+				// is any chunk of this splat live?  (bits of the 8 lanes of this slot in the ballot)
+				const unsigned grp = (any_live >> (lane & 24)) & 0xffu;
 				// the conic / opacity of the splat: lanes that were not live did not load the record (all lanes shuffle)
-				const int srcl = grp != 0u ? g0 + (__ffs(grp) - 1) : lane;
+				const int srcl = grp != 0u ? (lane & 24) + (__ffs(grp) - 1) : lane;
 				const float ca = __shfl_sync(0xffffffffu, r0.z, srcl), cb = __shfl_sync(0xffffffffu, r0.w, srcl);
 				const float cc = __shfl_sync(0xffffffffu, r1.x, srcl), op = __shfl_sync(0xffffffffu, r1.y, srcl);
-				if (grp != 0u && p2_slot < cnt && p2_chunk < 8) {
-					const uint32_t gid = ldu(sb + kOffId + ((uint32_t)(b % 3) * kB2 + (uint32_t)p2_slot) * 4u);
+				if (grp != 0u && p2_slot < cnt) {
+					const uint32_t gid = ldu(sb + kOffId + (uint32_t)(buf * kB2 + p2_slot) * 4u);
 					float *dst = grad2d + (size_t)gid * 12;
 					float o0, o1 = 0.f;
 					switch (p2_chunk) {  // lane c of the group writes components c and c + 8
@@ -266,32 +246,23 @@ __global__ void __launch_bounds__(256, (kB2 <= 8 ? 4 : 3)) blend_bwd2_kernel(con
 				}
 			}
 		}
+		if (b + 1 < nb) stash((b + 1) & 1);
 	}
 }
 
 cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView img, const float *out_alpha, const float *dL_dcolor,
                               const float *dL_ddepth, const float *dL_dalpha, float *grad2d, cudaStream_t st, bool grad2d_zeroed) {
 	if (f.P == 0) return cudaSuccess;
+	// (grad2d_zeroed: sgr_sharded_forward already cleared the rows this band can touch — see count_tiles_kernel)
 	cudaError_t e = grad2d_zeroed ? cudaSuccess : cudaMemsetAsync(grad2d, 0, (size_t)f.P * 12 * sizeof(float), st);
 	if (e != cudaSuccess) return e;
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
-	static const int batch = [] {
-		const char *v = getenv("SGR_BWD2_BATCH");
-		const int b = v ? atoi(v) : 16;
-		return (b == 8 || b == 16 || b == 32) ? b : 16;
-	}();
+	static std::atomic<uint64_t> configured{0};
+	if ((e = ensure_dynamic_smem(blend_bwd2_kernel, (int)kSmem2, configured)) != cudaSuccess) return e;
 	count_launch();
-#define SGR_LAUNCH_BWD2(B)                                                                                                         \
-	{                                                                                                                              \
-		static std::atomic<uint64_t> configured{0};                                                                                \
-		if ((e = ensure_dynamic_smem(blend_bwd2_kernel<B>, (int)Bwd2Layout<B>::total, configured)) != cudaSuccess) return e;       \
-		blend_bwd2_kernel<B><<<dim3(f.gx, rows), 256, Bwd2Layout<B>::total, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, \
-		                                                                          img.tile_max_contrib, out_alpha, dL_dcolor,      \
-		                                                                          dL_ddepth, dL_dalpha, grad2d);                   \
-	}
-	if (batch == 8) SGR_LAUNCH_BWD2(8) else if (batch == 32) SGR_LAUNCH_BWD2(32) else SGR_LAUNCH_BWD2(16)
-#undef SGR_LAUNCH_BWD2
+	blend_bwd2_kernel<<<dim3(f.gx, rows), 256, kSmem2, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, img.tile_max_contrib, out_alpha,
+	                                                         dL_dcolor, dL_ddepth, dL_dalpha, grad2d);
 	return cudaGetLastError();
 }
 

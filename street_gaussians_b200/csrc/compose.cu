@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) compose_bwd_kernel(const SegTable t, cons
 			const float *ps = poses + (size_t)(t.first + s) * 8;
 			const float4 qo = make_float4(ps[0], ps[1], ps[2], ps[3]);
 			const bool fl = flip != nullptr && flip[i] != 0;
-			const float4 fq = make_float4(flip_quat[0], flip_quat[1], flip_quat[2], flip_quat[3]);
+			const float4 fq = fl ? make_float4(flip_quat[0], flip_quat[1], flip_quat[2], flip_quat[3]) : make_float4(1.f, 0.f, 0.f, 0.f);
 			const float4 b = fl ? qmul(fq, n) : n;
 			const float4 y = qmul(qo, b);
 			const float yn = qnorm_clamped(y);
