@@ -312,7 +312,8 @@ int sgr_densify_stats(const SgrStatSegment *segments, int32_t num_segments, cons
 /* One multi-tensor Adam step (GaussianModel.update_optimizer -> torch.optim.Adam.step, lib/models/gaussian_model.py:300-303, 316-318:
  * no weight decay, no amsgrad): for each tensor  m <- m + (g - m)(1 - beta1);  v <- beta2 v + (1 - beta2) g^2;
  * param <- param - lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).  `step` is the 1-based step count AFTER
- * this update (torch increments before use).  tensors: HOST array; every pointer device, fp32, `numel` elements. */
+ * this update (torch increments before use).  betas / eps are doubles because torch forms 1 - beta in Python floats before it
+ * rounds to fp32 (1 - 0.999f differs from 0.001f by 1.3e-5 relative).  tensors: HOST array; every pointer device, fp32, `numel` elements. */
 typedef struct SgrAdamTensor {
 	float *param;
 	const float *grad;
@@ -321,7 +322,7 @@ typedef struct SgrAdamTensor {
 	float lr;
 	int32_t step;
 } SgrAdamTensor;
-int sgr_adam_step(const SgrAdamTensor *tensors, int32_t num_tensors, float beta1, float beta2, float eps, void *stream);
+int sgr_adam_step(const SgrAdamTensor *tensors, int32_t num_tensors, double beta1, double beta2, double eps, void *stream);
 
 /* present[P] (uint8 0/1) = view-space z > 0.2.  Replaces markVisible -> checkFrustum
  * (DGR/rasterize_points.cu:222-241, rasterizer_impl.cu:54-66, 141-153; pybind `mark_visible`, DGR/ext.cpp:18). */

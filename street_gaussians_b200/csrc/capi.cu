@@ -673,14 +673,14 @@ int sgr_densify_stats(const SgrStatSegment *segments, int32_t num_segments, cons
 	return SGR_OK;
 }
 
-int sgr_adam_step(const SgrAdamTensor *tensors, int32_t num_tensors, float beta1, float beta2, float eps, void *stream) {
+int sgr_adam_step(const SgrAdamTensor *tensors, int32_t num_tensors, double beta1, double beta2, double eps, void *stream) {
 	if (num_tensors < 0 || (num_tensors > 0 && !tensors)) return fail(SGR_EINVAL, "bad tensor table");
 	for (int k = 0; k < num_tensors; k++) {
 		const SgrAdamTensor &a = tensors[k];
 		if (a.numel < 0 || a.step < 1) return fail(SGR_EINVAL, "tensor %d: numel %lld, step %d (step counts from 1)", k, (long long)a.numel, a.step);
 		if (a.numel > 0 && (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq)) return fail(SGR_EINVAL, "tensor %d has a NULL pointer", k);
 	}
-	if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f)) return fail(SGR_EINVAL, "betas must lie in [0, 1)");
+	if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0)) return fail(SGR_EINVAL, "betas must lie in [0, 1)");
 	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 	const bool debug = false;
 	SGR_TRY(launch_adam(tensors, num_tensors, beta1, beta2, eps, st), "adam");

@@ -74,7 +74,8 @@ struct AdamTable {
 	int block_start[kAdamTensors + 1];  // first block of each tensor
 };
 
-__global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const float b1, const float b2, const float eps) {
+// omb1 = fl(1 - beta1), omb2 = fl(1 - beta2) formed in double on the host, exactly the scalars torch hands to lerp_ / addcmul_
+__global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const float omb1, const float b2, const float omb2, const float eps) {
 	int k = 0;  // tensor of this block (linear search: <= 48 entries, warp-uniform)
 	while (k + 1 < t.n && (int)blockIdx.x >= t.block_start[k + 1]) k++;
 	const long long base = (long long)(blockIdx.x - t.block_start[k]) * kAdamChunk;
@@ -85,15 +86,15 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, const floa
 	const float ss = t.step_size[k], ibc2 = t.inv_sqrt_bc2[k];
 	for (long long i = base + threadIdx.x; i < base + kAdamChunk && i < n; i += 256) {
 		const float gi = g[i];
-		const float mi = m[i] + (gi - m[i]) * (1.f - b1);        // exp_avg.lerp_(grad, 1 - beta1)
-		const float vi = v[i] * b2 + (1.f - b2) * gi * gi;       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+		const float mi = m[i] + (gi - m[i]) * omb1;              // exp_avg.lerp_(grad, 1 - beta1)
+		const float vi = v[i] * b2 + omb2 * gi * gi;             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
 		m[i] = mi;
 		v[i] = vi;
 		p[i] = p[i] - ss * (mi / (sqrtf(vi) * ibc2 + eps));      // param.addcdiv_(exp_avg, sqrt(v)/sqrt(bc2) + eps, value = -step_size)
 	}
 }
 
-cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, float beta1, float beta2, float eps, cudaStream_t st) {
+cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, double beta1, double beta2, double eps, cudaStream_t st) {
 	for (int first = 0; first < n_tensors; first += kAdamTensors) {
 		AdamTable t;
 		const int n = n_tensors - first < kAdamTensors ? n_tensors - first : kAdamTensors;
@@ -102,7 +103,7 @@ cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, float beta1, flo
 		for (int k = 0; k < n; k++) {
 			const SgrAdamTensor &a = ts[first + k];
 			t.p[k] = a.param; t.g[k] = a.grad; t.m[k] = a.exp_avg; t.v[k] = a.exp_avg_sq; t.numel[k] = a.numel;
-			const double bc1 = 1.0 - pow((double)beta1, (double)a.step), bc2 = 1.0 - pow((double)beta2, (double)a.step);
+			const double bc1 = 1.0 - pow(beta1, (double)a.step), bc2 = 1.0 - pow(beta2, (double)a.step);
 			t.step_size[k] = (float)((double)a.lr / bc1);
 			t.inv_sqrt_bc2[k] = (float)(1.0 / sqrt(bc2));
 			t.block_start[k] = blocks;
@@ -111,7 +112,7 @@ cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, float beta1, flo
 		t.block_start[n] = blocks;
 		if (blocks == 0) continue;
 		count_launch();
-		adam_kernel<<<blocks, 256, 0, st>>>(t, beta1, beta2, eps);
+		adam_kernel<<<blocks, 256, 0, st>>>(t, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps);
 	}
 	return cudaGetLastError();
 }

@@ -274,7 +274,7 @@ cudaError_t launch_image_loss(int C, int H, int W, const float *img, const float
                               float *scalars, void *scratch, cudaStream_t st);
 cudaError_t launch_sky_loss(size_t N, const float *accm, const uint8_t *sky, float weight, float *grad, float *scalars, void *scratch, cudaStream_t st);
 cudaError_t launch_densify_stats(const SgrStatSegment *segs, int nseg, const int32_t *radii, const float *grad2d, cudaStream_t st);
-cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, float beta1, float beta2, float eps, cudaStream_t st);
+cudaError_t launch_adam(const SgrAdamTensor *ts, int n_tensors, double beta1, double beta2, double eps, cudaStream_t st);
 size_t knn_scratch_bytes(int P);
 cudaError_t launch_knn(int P, const float *points, float *out, void *scratch, size_t scratch_bytes, cudaStream_t st);
 

@@ -363,7 +363,7 @@ def test_gaussian_sharded_emulated_ranks_match_single_gpu(S, world, layout):
             assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, i
 
 
-@pytest.mark.parametrize("world,compact", [(3, True), (2, False), (4, True)])
+@pytest.mark.parametrize("world,compact", [(3, True), (2, False), (4, True), (2, True), (4, False)])
 def test_fused_sharded_step_emulated_ranks(world, compact):
     """sgr_sharded_forward / sgr_sharded_backward (ONE C-ABI call each: project+scatter, device barrier, compacted depth sort, bin,
     blend | blend_bwd, device barrier, chain rule with the peer gather folded in) with the N ranks' workspaces on ONE GPU.  Each
@@ -382,6 +382,7 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
         ws.buf[: ws.off_flags].fill_(0x7f)  # poison everything but the barrier pads
     streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
     L = _capi.lib()
+    n_sel_seen = [0]
     for fi, scene in enumerate(frames):
         st = util.settings_from(sgb, scene["cam"], dev)
         t = {k: scene[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations", "grad_color", "grad_depth", "grad_alpha")}
@@ -401,7 +402,9 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
                     P_r = int(local[r]["means3D"].shape[0])
-                    gcap = (chunk * world) // 2 if compact else -1
+                    # depth-order slots of the compacted mode: every slot on the first frame (what the host does before it has seen a
+                    # count), the learnt count + headroom afterwards
+                    gcap = (chunk * world if fi == 0 else int(1.25 * max(n_sel_seen)) + 64) if compact else -1
                     outs.append(SH.sharded_forward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], P_r, capacity, gcap, status[r]))
             torch.cuda.synchronize()
             imgs = [sum(o[i] for o in outs) for i in range(3)]
@@ -423,13 +426,18 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
                     grads.append(SH.sharded_backward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], P_r, capacity, outs[r][2],
                                                          t["grad_color"], t["grad_depth"], t["grad_alpha"]))
             torch.cuda.synchronize()
+            # the partial sums every rank left in its workspace add up to the single-GPU grad2d (rows a rank never received are stale)
+            part = sum(torch.where((ws.radii_all[:P] > 0)[:, None], ws.grad2d[:P], torch.zeros_like(ws.grad2d[:P])).double() for ws in wss)
+            assert util.rel_err(part.cpu().numpy(), g2d.double().cpu().numpy()) < 1e-5, f"frame {fi}: partial grad2d sums"
             for i, ref in enumerate(ref_grads):
                 if ref is None:
                     assert all(g[i] is None for g in grads)
                     continue
                 got = torch.cat([g[i] for g in grads])
                 assert got.shape == ref.shape
-                assert util.rel_err(got.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5, (fi, i)
+                bad = [r for r in range(world)
+                       if util.rel_err(grads[r][i].double().cpu().numpy(), ref[r * chunk: r * chunk + grads[r][i].shape[0]].double().cpu().numpy()) >= 2e-5]
+                assert not bad, f"frame {fi}, output {i}: ranks {bad} differ from the single-GPU gradients"
     # a forward that follows a forward (no backward): the leading barrier of sgr.h is taken (epochs advance by 2)
     with torch.no_grad():
         e0 = [ws.epoch for ws in wss]

@@ -63,7 +63,9 @@ def run_case(rank, world, dev, S, P, W, H, bounded, exchange="nccl"):
     cap = sgb.InstanceCapacity() if bounded else None
     rast = GaussianShardedRasterizer(st, capacity=cap, exchange=exchange)
     worst = 0.0
-    for rep in range(2 if bounded else 1):  # second pass of the bounded variant runs without any host sync
+    # bounded variant: pass 1 is exact (learns the instance capacity); with exchange='p2p' pass 2 is the first FUSED frame
+    # (sgr_sharded_forward / sgr_sharded_backward, depth order compacted into all slots), passes 3-4 run with the learnt Gaussian capacity
+    for rep in range(4 if bounded else 1):
         loc = {k: scene[k][lo:hi].to(dev).requires_grad_(True) for k in KEYS}
         sem_loc = scene["semantics"][lo:hi].to(dev).requires_grad_(True) if S else None
         m2d = torch.zeros(hi - lo, 3, device=dev, requires_grad=True)
@@ -89,6 +91,13 @@ def run_case(rank, world, dev, S, P, W, H, bounded, exchange="nccl"):
         if S:
             e = util.rel_err(sem_loc.grad.double().cpu().numpy(), sem_full.grad[lo:hi].double().cpu().numpy())
             assert e < GRAD_TOL, ("semantics", e)
+    if bounded:  # forward-only frames back to back (eval loop): the leading barrier of the fused path / the staged path's extra barrier
+        with torch.no_grad():
+            for _ in range(3):
+                got = rast(means3D=loc["means3D"], means2D=None, opacities=loc["opacities"], shs=loc["shs"], scales=loc["scales"],
+                           rotations=loc["rotations"], semantics=sem_loc)
+                assert torch.equal(got[0][:, rows], ref[0].detach()[:, rows]), "no_grad forward: own rows differ"
+        rast.synchronize_capacity()
     return worst, floor
 
 
