@@ -116,9 +116,10 @@ int sgr_forward_bounded(const SgrFrame *frame, const float *means3D, const float
 /* Device->host copy of the status words of the last forward that used geom_state; synchronises `stream`.  `overflowed` is a bit
  * set: 1 = more instances than `capacity`, 2 = more Gaussians in the band than `gaussian_capacity` (sgr_sharded_forward). */
 int sgr_forward_status(const SgrFrame *frame, const void *geom_state, int64_t *num_instances, int32_t *overflowed, void *stream);
-/* Asynchronous variant: enqueues the copy of FOUR uint32 {instances, overflow bits, instances emitted, Gaussians with instances
- * (compacted mode, else 0)} into host_status (pinned host memory recommended) on `stream` and returns immediately; valid once
- * the caller has observed stream progress past this point. */
+/* Asynchronous variant: enqueues the copy of EIGHT uint32 {instances, overflow bits, instances emitted, Gaussians with instances
+ * (compacted mode, else 0), epoch of a device barrier that TIMED OUT in this forward (0 = none; sgr_sharded_forward), 3 reserved}
+ * into host_status (pinned host memory recommended) on `stream` and returns immediately; valid once the caller has observed
+ * stream progress past this point. */
 int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint32_t *host_status, void *stream);
 
 /* Backward, stage 1 of 2: per-pixel backward blend.  Replaces BACKWARD::render

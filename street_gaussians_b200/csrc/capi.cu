@@ -470,16 +470,16 @@ int sgr_forward_status_async(const SgrFrame *frame, const void *geom_state, uint
 	int rc = make_frame(frame, f);
 	if (rc) return rc;
 	if (!geom_state || !host_status) return fail(SGR_EINVAL, "NULL pointer passed to sgr_forward_status_async");
-	host_status[0] = host_status[1] = host_status[2] = host_status[3] = 0;
+	for (int k = 0; k < 8; k++) host_status[k] = 0;
 	if (f.P == 0) return SGR_OK;
 	const GeomView g = carve_geom(const_cast<void *>(geom_state), f.P);
-	cudaError_t e = cudaMemcpyAsync(host_status, g.big_count + 1, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream));
+	cudaError_t e = cudaMemcpyAsync(host_status, g.big_count + 1, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream));
 	if (e != cudaSuccess) return fail(SGR_ECUDA, "status copy: %s", cudaGetErrorString(e));
 	return SGR_OK;
 }
 
 int sgr_forward_status(const SgrFrame *frame, const void *geom_state, int64_t *num_instances, int32_t *overflowed, void *stream) {
-	uint32_t h[4] = {0, 0, 0, 0};
+	uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	int rc = sgr_forward_status_async(frame, geom_state, h, stream);
 	if (rc) return rc;
 	cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));

@@ -64,27 +64,49 @@ struct Projected {
 	int x0, y0, x1, y1;
 };
 
-// Shared front half of preprocess / visible_filter: cull, project, conic, radius, tile rectangle.
-__device__ __forceinline__ Projected project_gaussian(const FrameDev &f, int idx, const float3 p, const float *__restrict__ scales,
-                                                      const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp) {
+// The per-Gaussian shape inputs, loaded at the TOP of the kernels together with the position and the opacity: the round-1 kernel
+// loaded them where they were used (after the near cull, inside the projection), which serialised three DRAM round trips per
+// thread (ncu source view, profiles/r02_summary.md: 38 % of the warp stalls were long-scoreboard waits on exactly these loads).
+struct ShapeIn {
+	float3 s;
+	float4 q;
+	float c6[6];
+};
+__device__ __forceinline__ ShapeIn load_shape(int idx, const float *__restrict__ scales, const float *__restrict__ rotations,
+                                              const float *__restrict__ cov3D_precomp) {
+	ShapeIn g;
+	g.s = make_float3(0.f, 0.f, 0.f);
+	g.q = make_float4(1.f, 0.f, 0.f, 0.f);
+	if (cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) g.c6[k] = cov3D_precomp[6 * (size_t)idx + k];
+	} else {
+		g.s = make_float3(scales[3 * (size_t)idx], scales[3 * (size_t)idx + 1], scales[3 * (size_t)idx + 2]);
+		g.q = *reinterpret_cast<const float4 *>(rotations + 4 * (size_t)idx);
+	}
+	return g;
+}
+
+// Shared front half of preprocess / visible_filter: cull, project, conic, radius, tile rectangle.  `view` / `proj` may point at
+// a shared-memory copy of the camera matrices.
+__device__ __forceinline__ Projected project_gaussian(const FrameDev &f, const float *view, const float *proj, const float3 p, ShapeIn g,
+                                                      const bool precomp) {
 	Projected o;
 	o.ok = false;
 	o.radius = 0;
-	const float4 p_hom = xform4x4(p, f.proj);
+	const float4 p_hom = xform4x4(p, proj);
 	const float p_w = 1.0f / (p_hom.w + 0.0000001f);
 	const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
-	const float3 p_view = xform4x3(p, f.view);
+	const float3 p_view = xform4x3(p, view);
 	if (p_view.z <= 0.2f) return o;  // near cull only (reference auxiliary.h:154)
 	float c6[6];
-	if (cov3D_precomp != nullptr) {
+	if (precomp) {
 #pragma unroll
-		for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * (size_t)idx + k];
+		for (int k = 0; k < 6; k++) c6[k] = g.c6[k];
 	} else {
-		const float3 s = make_float3(scales[3 * (size_t)idx], scales[3 * (size_t)idx + 1], scales[3 * (size_t)idx + 2]);
-		const float4 q = *reinterpret_cast<const float4 *>(rotations + 4 * (size_t)idx);
-		cov3d_from_scale_rot(s, f.mod, q, c6);
+		cov3d_from_scale_rot(g.s, f.mod, g.q, c6);
 	}
-	const float3 cov = cov2d_ewa(p, f.fx, f.fy, f.tanx, f.tany, c6, f.view);
+	const float3 cov = cov2d_ewa(p, f.fx, f.fy, f.tanx, f.tany, c6, view);
 	const float det = (cov.x * cov.z - cov.y * cov.y);
 	if (det == 0.0f) return o;
 	const float det_inv = 1.f / det;
@@ -212,22 +234,34 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 			if (lane == 0) mbar_expect_tx(sh_bar, row_bytes * (uint32_t)rows);
 		}
 	}
+	// every small per-Gaussian input is requested up front, before any arithmetic: one DRAM round trip instead of three
 	Projected pr;
 	pr.ok = false;
 	pr.radius = 0;
 	CullParams cp = {};
 	float3 p = make_float3(0.f, 0.f, 0.f);
+	float opacity = 0.f;
+	ShapeIn shape;
 	if (in_range) {
 		p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
-		pr = project_gaussian(f, idx, p, scales, rotations, cov3D_precomp);
+		opacity = opacities[idx];
+		shape = load_shape(idx, scales, rotations, cov3D_precomp);
 	}
+	// camera constants through shared memory: every thread needs all 35 floats, and read through the settings' device pointers
+	// they were per-thread global loads at the head of the dependency chain
+	__shared__ float s_cam[36];
+	if (threadIdx.x < 16) s_cam[threadIdx.x] = f.view[threadIdx.x];
+	else if (threadIdx.x < 32) s_cam[threadIdx.x] = f.proj[threadIdx.x - 16];
+	else if (threadIdx.x < 35) s_cam[threadIdx.x] = f.campos[threadIdx.x - 32];
+	__syncthreads();
+	if (in_range) pr = project_gaussian(f, s_cam, s_cam + 16, p, shape, cov3D_precomp != nullptr);
 	if (TMA && sh_pending) mbar_wait(sh_bar, 0);  // all rows of the warp have landed (also keeps the CTA alive until they have)
 	if (in_range) {
 		if (pr.ok) {
 			float3 rgb;
 			uint32_t clamp_bits = 0;
 			if (colors_precomp == nullptr) {
-				const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
+				const float3 campos = make_float3(s_cam[32], s_cam[33], s_cam[34]);
 				float c[48];
 				const int n = min(f.M, (f.D + 1) * (f.D + 1)) * 3;
 				if (TMA) load_sh_smem(c, sh_row, n);
@@ -236,7 +270,6 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 			} else {
 				rgb = make_float3(colors_precomp[3 * (size_t)idx], colors_precomp[3 * (size_t)idx + 1], colors_precomp[3 * (size_t)idx + 2]);
 			}
-			const float opacity = opacities[idx];
 			GaussRec r;
 			cp = make_cull(pr.px, pr.py, pr.conic.x, pr.conic.y, pr.conic.z, opacity);
 			r.q0 = make_float4(pr.px, pr.py, pr.conic.x, pr.conic.y);
@@ -278,7 +311,7 @@ __global__ void __launch_bounds__(256) filter_kernel(const FrameDev f, const flo
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= f.P) return;
 	const float3 p = make_float3(means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]);
-	const Projected pr = project_gaussian(f, idx, p, scales, rotations, cov3D_precomp);
+	const Projected pr = project_gaussian(f, f.view, f.proj, p, load_shape(idx, scales, rotations, cov3D_precomp), cov3D_precomp != nullptr);
 	radii[idx] = pr.radius;
 	means2D[2 * (size_t)idx] = pr.ok ? pr.px : 0.f;
 	means2D[2 * (size_t)idx + 1] = pr.ok ? pr.py : 0.f;

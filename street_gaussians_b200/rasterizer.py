@@ -119,8 +119,8 @@ class InstanceCapacity:
             self.gaussian_capacity = want
 
     def status_word(self) -> torch.Tensor:
-        """A pinned int32[4] for sgr_forward_status_async; recycled once its frame has been checked."""
-        return self._pool.pop() if self._pool else torch.zeros(4, dtype=torch.int32).pin_memory()
+        """A pinned int32[8] for sgr_forward_status_async; recycled once its frame has been checked."""
+        return self._pool.pop() if self._pool else torch.zeros(8, dtype=torch.int32).pin_memory()
 
     def track(self, host_status: torch.Tensor, event):
         self._pending.append((host_status, event))
@@ -137,8 +137,12 @@ class InstanceCapacity:
             if not ev.query():
                 self._pending.append((host_status, ev))
                 continue
-            R, overflow, n_sel = int(host_status[0]), int(host_status[1]), int(host_status[3])
+            R, overflow, n_sel, timed_out = int(host_status[0]), int(host_status[1]), int(host_status[3]), int(host_status[4])
             self._pool.append(host_status)
+            if timed_out:
+                self._pending.extend(pending[i + 1:])
+                raise _capi.SgrError(f"the device barrier of epoch {timed_out} timed out (a peer rank never arrived within 2 s): that frame "
+                                     "was rendered from incomplete peer data")
             old, old_g = self.capacity, self.gaussian_capacity
             self.observe(R)
             if n_sel:

@@ -398,7 +398,7 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
                 sl = slice(r * chunk, min(P, (r + 1) * chunk))
                 local.append(SH._local_tensors(t["means3D"][sl], t["shs"][sl], None, None, t["opacities"][sl], t["scales"][sl],
                                                t["rotations"][sl], None))
-                status.append(torch.zeros(4, dtype=torch.int32).pin_memory())
+                status.append(torch.zeros(8, dtype=torch.int32).pin_memory())
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
                     P_r = int(local[r]["means3D"].shape[0])
@@ -407,12 +407,15 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
                     gcap = (chunk * world if fi == 0 else int(1.25 * max(n_sel_seen)) + 64) if compact else -1
                     outs.append(SH.sharded_forward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], P_r, capacity, gcap, status[r]))
             torch.cuda.synchronize()
+            for r in range(world):
+                assert int(status[r][4]) == 0, f"rank {r}: device barrier of epoch {int(status[r][4])} timed out (ranks not co-scheduled)"
             imgs = [sum(o[i] for o in outs) for i in range(3)]
             for a, b, name in zip(imgs, (col, dep, alp), ("color", "depth", "alpha")):
                 assert torch.equal(a, b), f"frame {fi}: {name} differs from the single-GPU render"
             n_sel_total = 0
             for r in range(world):
-                R_r, over, emitted, n_sel = (int(v) for v in status[r])
+                R_r, over, emitted, n_sel, timed_out = (int(v) for v in status[r][:5])
+                assert timed_out == 0, f"rank {r}: the device barrier of epoch {timed_out} timed out (ranks not co-scheduled on this GPU)"
                 assert over == 0 and R_r == emitted and R_r <= fst.num_instances
                 assert (n_sel > 0) == compact
                 n_sel_total += n_sel
@@ -459,7 +462,7 @@ def test_gaussian_capacity_overflow_is_flagged():
     ws = SH.PeerWorkspace.emulate(st, P, 1, dev)[0]
     lt = SH._local_tensors(scene["means3D"].to(dev), scene["shs"].to(dev), None, None, scene["opacities"].to(dev), scene["scales"].to(dev),
                            scene["rotations"].to(dev), None)
-    hs = torch.zeros(4, dtype=torch.int32).pin_memory()
+    hs = torch.zeros(8, dtype=torch.int32).pin_memory()
     with torch.no_grad():
         SH.sharded_forward_raw(st, None, ws, lt, P, 2_000_000, 100, hs)
     torch.cuda.synchronize()
