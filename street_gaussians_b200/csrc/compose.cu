@@ -69,6 +69,37 @@ __device__ __forceinline__ bool warp_is_contiguous(int seg, int li, bool active)
 	return __all_sync(full, active && seg == s0 && li == l0 + lane);
 }
 
+// Warp-cooperative copy of 32 rows of R3 floats between a dense block (row stride R3) and rows embedded at `off` in rows of stride
+// `wide`.  Loads are issued in batches of kCopyBatch before the dependent stores: the naive "load one, store one" loop kept ONE
+// request in flight per lane and left the composer at 0.4-0.67 of the HBM roofline (ncu: 78 % long-scoreboard stalls on the store).
+constexpr int kCopyBatch = 9;
+template <bool TO_WIDE>
+__device__ __forceinline__ void warp_copy_rows(const float *__restrict__ src, float *__restrict__ dst, const int R3, const int wide, const int off,
+                                               const int lane) {
+	const int total = 32 * R3;
+	int row = lane / R3, col = lane - row * R3;  // position of element e = lane in the dense block
+	for (int e0 = lane; e0 < total; e0 += 32 * kCopyBatch) {
+		float v[kCopyBatch];
+		int r[kCopyBatch], c[kCopyBatch];
+#pragma unroll
+		for (int u = 0; u < kCopyBatch; u++) {
+			const int e = e0 + 32 * u;
+			r[u] = row; c[u] = col;
+			if (e < total) v[u] = TO_WIDE ? __ldg(src + e) : __ldg(src + (size_t)row * wide + off + col);
+			col += 32;
+			while (col >= R3) { col -= R3; row++; }
+		}
+#pragma unroll
+		for (int u = 0; u < kCopyBatch; u++) {
+			const int e = e0 + 32 * u;
+			if (e < total) {
+				if (TO_WIDE) dst[(size_t)r[u] * wide + off + c[u]] = v[u];
+				else dst[e] = v[u];
+			}
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256) compose_fwd_kernel(const SegTable t, const int M, const float *__restrict__ poses,
                                                          const float *__restrict__ idft, const uint8_t *__restrict__ flip,
                                                          const float *__restrict__ flip_quat, float *__restrict__ o_xyz,
@@ -83,8 +114,14 @@ __global__ void __launch_bounds__(256) compose_fwd_kernel(const SegTable t, cons
 		li = i - t.start[s];
 		const SegDev sg = t.seg[s];
 		const size_t l = (size_t)li, g = (size_t)i;
+		// all per-Gaussian inputs are requested before any arithmetic (one DRAM round trip)
 		float3 p = make_float3(sg.xyz[3 * l], sg.xyz[3 * l + 1], sg.xyz[3 * l + 2]);
 		float4 q = *reinterpret_cast<const float4 *>(sg.rotation + 4 * l);
+		const float3 ls = make_float3(sg.scaling[3 * l], sg.scaling[3 * l + 1], sg.scaling[3 * l + 2]);
+		const float lo = sg.opacity[l];
+		const int C = t.fourier[s];
+		const float *fd = sg.fdc + l * C * 3;
+		const float3 dc0 = make_float3(fd[0], fd[1], fd[2]);
 		const float qn = qnorm_clamped(q);
 		q = make_float4(q.x / qn, q.y / qn, q.z / qn, q.w / qn);  // gaussian_model.py:229-230
 		if (t.posed[s]) {
@@ -105,20 +142,17 @@ __global__ void __launch_bounds__(256) compose_fwd_kernel(const SegTable t, cons
 		}
 		o_xyz[3 * g] = p.x; o_xyz[3 * g + 1] = p.y; o_xyz[3 * g + 2] = p.z;
 		*reinterpret_cast<float4 *>(o_rot + 4 * g) = q;
-		o_scale[3 * g] = expf(sg.scaling[3 * l]); o_scale[3 * g + 1] = expf(sg.scaling[3 * l + 1]); o_scale[3 * g + 2] = expf(sg.scaling[3 * l + 2]);
-		o_opac[g] = 1.0f / (1.0f + expf(-sg.opacity[l]));
+		o_scale[3 * g] = expf(ls.x); o_scale[3 * g + 1] = expf(ls.y); o_scale[3 * g + 2] = expf(ls.z);
+		o_opac[g] = 1.0f / (1.0f + expf(-lo));
 		// DC colour: background = its single row; actors = sum_c dc[c] * IDFT(t)[c] (gaussian_model_actor.py:76-77)
-		const int C = t.fourier[s];
-		float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+		float d0 = dc0.x, d1 = dc0.y, d2 = dc0.z;
 		if (t.posed[s]) {
 			const float *w = idft + (size_t)(t.first + s) * SGR_MAX_FOURIER;
-			for (int c = 0; c < C; c++) {
-				const float *f = sg.fdc + (l * C + c) * 3;
+			d0 *= w[0]; d1 *= w[0]; d2 *= w[0];
+			for (int c = 1; c < C; c++) {
+				const float *f = fd + c * 3;
 				d0 += f[0] * w[c]; d1 += f[1] * w[c]; d2 += f[2] * w[c];
 			}
-		} else {
-			const float *f = sg.fdc + l * C * 3;
-			d0 = f[0]; d1 = f[1]; d2 = f[2];
 		}
 		float *dst = o_sh + g * M * 3;
 		dst[0] = d0; dst[1] = d1; dst[2] = d2;
@@ -128,12 +162,7 @@ __global__ void __launch_bounds__(256) compose_fwd_kernel(const SegTable t, cons
 	if (R3 <= 0) return;
 	if (warp_is_contiguous(s, li, active)) {
 		const int s0 = __shfl_sync(0xffffffffu, s, 0), l0 = __shfl_sync(0xffffffffu, li, 0), i0 = __shfl_sync(0xffffffffu, i, 0);
-		const float *src = t.seg[s0].frest + (size_t)l0 * R3;
-		float *dst = o_sh + (size_t)i0 * M * 3;
-		for (int e = lane; e < 32 * R3; e += 32) {
-			const int row = e / R3, col = e - row * R3;
-			dst[(size_t)row * (M * 3) + 3 + col] = __ldg(src + e);
-		}
+		warp_copy_rows<true>(t.seg[s0].frest + (size_t)l0 * R3, o_sh + (size_t)i0 * M * 3, R3, M * 3, 3, lane);
 	} else if (active) {
 		const float *src = t.seg[s].frest + (size_t)li * R3;
 		float *dst = o_sh + (size_t)i * M * 3 + 3;
@@ -164,14 +193,21 @@ __global__ void __launch_bounds__(256) compose_bwd_kernel(const SegTable t, cons
 		const SegDev sg = t.seg[s];
 		const SegGradDev og = gt.seg[s];
 		const size_t l = (size_t)li, g = (size_t)i;
+		// all per-Gaussian inputs are requested before any arithmetic or store (one DRAM round trip)
+		const float3 ls = make_float3(sg.scaling[3 * l], sg.scaling[3 * l + 1], sg.scaling[3 * l + 2]);
+		const float3 gs = make_float3(g_scale[3 * g], g_scale[3 * g + 1], g_scale[3 * g + 2]);
+		const float lo = sg.opacity[l], go = g_opac[g];
+		const float gd0 = g_sh[g * M * 3], gd1 = g_sh[g * M * 3 + 1], gd2 = g_sh[g * M * 3 + 2];
+		const float4 raw = *reinterpret_cast<const float4 *>(sg.rotation + 4 * l);
+		float4 gn = *reinterpret_cast<const float4 *>(g_rot + 4 * g);  // gradient w.r.t. the composed (unit) rotation
+		float3 gx = make_float3(g_xyz[3 * g], g_xyz[3 * g + 1], g_xyz[3 * g + 2]);
+		float3 xl = posed ? make_float3(sg.xyz[3 * l], sg.xyz[3 * l + 1], sg.xyz[3 * l + 2]) : make_float3(0.f, 0.f, 0.f);
 		// activations (gaussian_model.py:224-251): d exp = exp, d sigmoid = o (1 - o)
-#pragma unroll
-		for (int k = 0; k < 3; k++) og.scaling[3 * l + k] = g_scale[3 * g + k] * expf(sg.scaling[3 * l + k]);
-		const float o = 1.0f / (1.0f + expf(-sg.opacity[l]));
-		og.opacity[l] = g_opac[g] * o * (1.f - o);
+		og.scaling[3 * l] = gs.x * expf(ls.x); og.scaling[3 * l + 1] = gs.y * expf(ls.y); og.scaling[3 * l + 2] = gs.z * expf(ls.z);
+		const float o = 1.0f / (1.0f + expf(-lo));
+		og.opacity[l] = go * o * (1.f - o);
 		// DC colour
 		const int C = t.fourier[s];
-		const float gd0 = g_sh[g * M * 3], gd1 = g_sh[g * M * 3 + 1], gd2 = g_sh[g * M * 3 + 2];
 		if (posed) {
 			const float *w = idft + (size_t)(t.first + s) * SGR_MAX_FOURIER;
 			for (int c = 0; c < C; c++) {
@@ -184,11 +220,8 @@ __global__ void __launch_bounds__(256) compose_bwd_kernel(const SegTable t, cons
 			for (int k = 3; k < C * 3; k++) f[k] = 0.f;  // (a background with C > 1 only ever uses row 0)
 		}
 		// rotation: z = normalize(y), y = q_obj (x) b, b = [flip_quat (x)] n, n = normalize(raw)
-		const float4 raw = *reinterpret_cast<const float4 *>(sg.rotation + 4 * l);
 		const float rn = qnorm_clamped(raw);
 		const float4 n = make_float4(raw.x / rn, raw.y / rn, raw.z / rn, raw.w / rn);
-		float4 gn = *reinterpret_cast<const float4 *>(g_rot + 4 * g);  // gradient w.r.t. the composed (unit) rotation
-		float3 gx = make_float3(g_xyz[3 * g], g_xyz[3 * g + 1], g_xyz[3 * g + 2]);
 		if (posed) {
 			const float *ps = poses + (size_t)(t.first + s) * 8;
 			const float4 qo = make_float4(ps[0], ps[1], ps[2], ps[3]);
@@ -206,7 +239,6 @@ __global__ void __launch_bounds__(256) compose_bwd_kernel(const SegTable t, cons
 			gn = gb;
 			a16[9] = ga.x; a16[10] = ga.y; a16[11] = ga.z; a16[12] = ga.w;
 			// position: x_w = R(q_obj) x_l + t
-			float3 xl = make_float3(sg.xyz[3 * l], sg.xyz[3 * l + 1], sg.xyz[3 * l + 2]);
 			if (fl) xl.y = -xl.y;
 			float R[9];
 			quat_to_rot(qo, R);
@@ -248,12 +280,7 @@ __global__ void __launch_bounds__(256) compose_bwd_kernel(const SegTable t, cons
 	if (R3 <= 0) return;
 	if (contiguous) {
 		const int s0 = __shfl_sync(full, s, 0), l0 = __shfl_sync(full, li, 0), i0 = __shfl_sync(full, i, 0);
-		float *dst = gt.seg[s0].frest + (size_t)l0 * R3;
-		const float *src = g_sh + (size_t)i0 * M * 3;
-		for (int e = lane; e < 32 * R3; e += 32) {
-			const int row = e / R3, col = e - row * R3;
-			dst[e] = __ldg(src + (size_t)row * (M * 3) + 3 + col);
-		}
+		warp_copy_rows<false>(g_sh + (size_t)i0 * M * 3, gt.seg[s0].frest + (size_t)l0 * R3, R3, M * 3, 3, lane);
 	} else if (active) {
 		float *dst = gt.seg[s].frest + (size_t)li * R3;
 		const float *src = g_sh + (size_t)i * M * 3 + 3;

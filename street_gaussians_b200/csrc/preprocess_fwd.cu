@@ -329,8 +329,13 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *_
 
 // TMA staging applies when the rows are 16-B multiples (M = 4, 8, 12, 16: SH degree 1 and 3) and 16-B aligned
 static bool sh_rows_fit_tma(const FrameDev &f, const float *shs) {
-	static const bool disabled = getenv("SGR_NO_TMA") != nullptr;  // A/B switch for profiling: per-thread global loads instead
-	if (disabled) return false;
+	// Measured on B200 (config C, profiles/r02_summary.md): with the small inputs requested up front the per-thread global-load
+	// path runs this kernel in 144 us; the TMA stage (one cp.async.bulk per lane — padded rows need per-row copies, which ptxas
+	// serialises into a 32-iteration uniform-datapath loop, +22 M warp-instructions in an issue-bound kernel) takes 156 us.  The
+	// forward therefore uses TMA only on request (SGR_FWD_TMA=1); the backward, where it replaced a latency-bound staging loop
+	// (252 -> 182 us, 0.58 -> 0.89 of the HBM roofline), uses it by default.
+	static const bool enabled = getenv("SGR_FWD_TMA") != nullptr && getenv("SGR_NO_TMA") == nullptr;
+	if (!enabled) return false;
 	return shs != nullptr && f.M > 0 && f.M <= 16 && (f.M * 12) % 16 == 0 && (reinterpret_cast<uintptr_t>(shs) & 15u) == 0;
 }
 constexpr size_t kFwdStageBytes = (size_t)8 * 32 * kShStride * sizeof(float) + 8 * sizeof(uint64_t);  // 53,312 B
