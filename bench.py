@@ -61,6 +61,11 @@ def parse():
                          "stage by stage from Python (round-1 path).  gaussian-p2p-allgather: gaussian-p2p followed by an NCCL all-gather of "
                          "every parameter gradient, so that EVERY rank ends with all gradients (the north-star's literal contract).  "
                          "replicated: parameters replicated, tile rows sharded, one all-reduce (ShardedGaussianRasterizer)")
+    ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
+                    help="timed region: capture ONE fwd+bwd step (through the public API, autograd included) in a CUDA graph after the warm-up "
+                         "and replay it K times — no per-kernel launch latency, no Python between kernels.  Needs the sync-free mode (nothing "
+                         "in the step may talk to the host); the Gaussian-sharded peer-memory step is graph-safe because its barrier epochs "
+                         "live on the device.  auto = on where supported, falling back to the eager loop if capture fails")
     ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--diag", action="store_true", help="per-rank host/all-reduce timing breakdown on stderr")
     ap.add_argument("--cpu-sample-stride", type=int, default=0, help="CPU baseline uses every k-th Gaussian (0 = auto)")
@@ -462,24 +467,74 @@ def main():
         step()
     diag["ar"].clear()
     barrier()
+    if not ref_cuda:
+        from street_gaussians_b200 import _capi as _sgr_capi
+
+    # ---- optional: the step as a CUDA graph ----
+    graph, graph_note, launches_per_replay = None, None, 0
+    graph_ok = (not ref_cuda and args.graph != "off" and args.sync_free and capacity is not None and capacity.capacity is not None
+                and not args.diag and (not use_dist or args.mp_mode == "gaussian-p2p"))
+    if graph_ok:
+        try:
+            capacity.freeze()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up on a side stream, as torch.cuda.graph requires
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            l0 = int(_sgr_capi.lib().sgr_launch_count())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                color, radii = step()
+            launches_per_replay = int(_sgr_capi.lib().sgr_launch_count()) - l0
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            graph, graph_note = None, f"capture failed, eager loop timed instead: {e!r}"[:300]
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+        if use_dist:  # every rank must take the same path (the device barriers pair replays with replays)
+            flag = torch.tensor([1 if graph is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                graph = None
+                graph_note = graph_note or "capture failed on another rank; eager loop timed instead"
+        if graph is None:
+            capacity.freeze(False)
+            for _ in range(3):
+                step()
+        barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.mark(0)
-    launches0 = 0
-    if not ref_cuda:
-        from street_gaussians_b200 import _capi as _sgr_capi
-        launches0 = int(_sgr_capi.lib().sgr_launch_count())
+    launches0 = int(_sgr_capi.lib().sgr_launch_count()) if not ref_cuda else 0
     e0.record()
     for _ in range(args.steps):
         t_h = time.perf_counter()
-        color, radii = step()
+        if graph is not None:
+            graph.replay()
+        else:
+            color, radii = step()
         diag["host"].append((time.perf_counter() - t_h) * 1e3)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    # kernels of libsgr.so enqueued by THIS rank inside the timed region (counted in the library, cub's sort / scan kernels excluded)
-    gpu_launches = (int(_sgr_capi.lib().sgr_launch_count()) - launches0) if not ref_cuda else 0
+    # kernels of libsgr.so enqueued by THIS rank inside the timed region (counted in the library at launch / capture time; cub's sort
+    # and scan kernels excluded)
+    if ref_cuda:
+        gpu_launches = 0
+    elif graph is not None:
+        gpu_launches = launches_per_replay * args.steps
+    else:
+        gpu_launches = int(_sgr_capi.lib().sgr_launch_count()) - launches0
     host_ms = float(np.median(diag["host"]))
+    if graph is not None:
+        capacity.freeze(False)  # the legs below (stage table, exact mode, e2e) run eagerly with tracking on
     if args.diag:
         ar = [a.elapsed_time(b) for a, b in diag["ar"]]
         print(f"[diag rank {rank}] step {ms_total / args.steps:.3f} ms | host loop per step: median {np.median(diag['host']):.3f} max {max(diag['host']):.3f} ms"
@@ -700,6 +755,10 @@ def main():
                              note="pinned host -> device copy of all 59 floats/Gaussian every step (each rank uploads the Gaussians it owns), double-buffered on a copy stream; scalar loss read back"),
                     gpu_launches=gpu_launches, clocks=clocks)
         line["config"]["host_ms_per_step"] = host_ms
+        line["config"]["timed_region"] = ("CUDA graph: one fwd+bwd step through the public API (autograd included) captured after the warm-up, "
+                                          "replayed %d times" % args.steps) if graph is not None else "eager Python loop"
+        if graph_note:
+            line["config"]["graph_note"] = graph_note
         if parity_n is not None:
             line["parity_n"] = parity_n
         if e2e_comp is not None:

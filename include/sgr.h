@@ -213,7 +213,10 @@ int sgr_gather_grad2d(const SgrFrame *frame, const SgrPeers *peers, const void *
 /* Device-side barrier across the ranks of `peers` on `stream` (no host involvement, no NCCL): each rank stores `epoch` into its
  * slot of every peer's pad (release, system scope, after fencing its earlier peer stores) and waits until every peer has stored
  * an epoch >= `epoch` into its own pad.  Every rank must issue the same sequence of barriers with epochs increasing by one
- * (first epoch 1).  The wait is bounded (2 s): a rank that never arrives cannot wedge the GPU. */
+ * (first epoch 1).  epoch == 0 selects the device-side count: the library keeps the epoch in the rank's own pad (slot
+ * SGR_MAX_PEERS) and increments it per barrier, so the call carries no per-step host value and a CUDA graph that captured a step
+ * can be replayed.  Do not mix explicit and automatic epochs on one pad.  The wait is bounded (2 s): a rank that never arrives
+ * cannot wedge the GPU. */
 int sgr_peer_barrier(const SgrPeers *peers, uint32_t epoch, void *stream);
 
 /* The Gaussian-sharded forward as ONE call (steps 1-3 above with the peer-memory exchange): project the rank's frame.P Gaussians and
@@ -226,8 +229,8 @@ int sgr_peer_barrier(const SgrPeers *peers, uint32_t epoch, void *stream);
  *   for sgr_sharded_backward).  Bounded mode only: `capacity` instances (binning_state of sgr_binning_bytes(capacity)) and
  *   `gaussian_capacity` depth-order slots (< 0: sort all world*chunk Gaussians; otherwise only the Gaussians with instances in
  *   this band are compacted and sorted — sgr_forward_status reports both counts and both overflow bits).
- *   barrier_epoch: epoch of the barrier after the scatter; with pre_barrier != 0 a barrier with epoch barrier_epoch - 1 is issued
- *   first (needed when the previous call on this workspace was a forward without a backward: peers may still be reading the
+ *   barrier_epoch: epoch of the barrier after the scatter (0 = device-side count, see sgr_peer_barrier); with pre_barrier != 0 a
+ *   barrier with epoch barrier_epoch - 1 (or the next device-side count) is issued first (needed when the previous call on this workspace was a forward without a backward: peers may still be reading the
  *   records this call overwrites).  The rows of peers->grad2d[rank] that a backward can touch are zeroed by this call. */
 int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const float *means3D, const float *shs, const float *colors_precomp,
                         const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp, float *out_color,

@@ -413,7 +413,7 @@ int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const floa
 	if (capacity > 0 && (!binning_state || binning_bytes < need))
 		return fail(SGR_ENOMEM, "binning_state too small for capacity %lld: %zu < %zu", (long long)capacity, binning_bytes, need);
 	// a forward that follows a forward (no backward in between) must not overwrite records a peer may still be blending
-	if (pre_barrier) SGR_TRY(launch_peer_barrier(pt, barrier_epoch - 1u, nullptr, st), "pre-barrier");
+	if (pre_barrier) SGR_TRY(launch_peer_barrier(pt, barrier_epoch ? barrier_epoch - 1u : 0u, nullptr, st), "pre-barrier");
 	SGR_TRY(launch_project_scatter(fl, pt, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii_local,
 	                               reinterpret_cast<GaussRec *>(records_local), st),
 	        "project+scatter");

@@ -68,10 +68,20 @@ __global__ void __launch_bounds__(256) gather_grad2d_kernel(const FrameDev f, co
 // scope, after a system-scope fence that orders this rank's earlier peer stores — issued by previous kernels of the stream —
 // before it) and then waits until rank p has announced itself in this rank's pad.  Epochs increase by one per barrier and every
 // rank issues the same sequence of barriers, so one pad suffices: a peer that is already one barrier ahead has written a larger
-// epoch, which also satisfies the wait.  The spin is bounded (2 s) so a missing peer cannot wedge the GPU; a timeout sets
-// status[5] and the frame is garbage.
-__global__ void peer_barrier_kernel(const PeerTable pt, const uint32_t epoch, uint32_t *__restrict__ status) {
+// epoch, which also satisfies the wait.  epoch == 0 ("auto"): the epoch is kept ON THE DEVICE — slot kMaxPeers of the rank's own pad
+// counts its barriers — so the launch carries no per-step host value and a captured CUDA graph of a step can be replayed.
+// The spin is bounded (2 s) so a missing peer cannot wedge the GPU; a timeout sets status[5] and the frame is garbage.
+__global__ void peer_barrier_kernel(const PeerTable pt, uint32_t epoch, uint32_t *__restrict__ status) {
 	const int p = threadIdx.x;
+	if (epoch == 0u) {
+		uint32_t e = 0u;
+		if (p == 0) {
+			uint32_t *counter = pt.flags[pt.rank] + kMaxPeers;
+			e = *counter + 1u;
+			*counter = e;
+		}
+		epoch = __shfl_sync(0xffffffffu, e, 0);
+	}
 	if (p >= pt.world) return;
 	__threadfence_system();
 	uint32_t *theirs = pt.flags[p] + pt.rank;

@@ -101,7 +101,10 @@ __device__ __forceinline__ void visit_tiles(bool active, int x0, int y0, int x1,
 		y1 = min(y1, band.end);
 		if (y1 <= y0 || cp.qmax < 0.f) active = false;
 	}
-	const int w = active ? (x1 - x0) : 0, h = active ? (y1 - y0) : 0;
+	// rows of the rectangle this process actually owns: with a cyclic band (row_step = number of ranks) only every step-th row is
+	// walked, so a rectangle that is "large" on one GPU is small per rank at N = 8 — without this every rank deferred (and walked
+	// warp-cooperatively) every large splat of the frame, and emit_big_kernel did not scale with N at all (profiles/r02_summary.md)
+	const int w = active ? (x1 - x0) : 0, h = active ? (y1 - y0 + band.step - 1) / band.step : 0;
 	const bool coop = w * h > kCoopArea;
 	const EllipseAux ea = ellipse_aux(cp);
 	count = 0;

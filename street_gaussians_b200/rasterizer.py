@@ -105,6 +105,7 @@ class InstanceCapacity:
     def __init__(self, headroom: float = 1.25, initial: Optional[int] = None):
         self.headroom, self.capacity = float(headroom), (int(initial) if initial else None)
         self.gaussian_capacity = None  # depth-order slots of the compacted Gaussian-sharded forward (sgr_sharded_forward)
+        self.frozen = False            # freeze(): capacities fixed, no per-frame status copy / event (CUDA-graph capture of a step)
         self._pending = []  # (pinned int32[4], cuda event) in submission order
         self._pool = []     # pinned status words ready for reuse: no pin_memory() (a cudaHostAlloc) inside the steady-state step
 
@@ -112,6 +113,15 @@ class InstanceCapacity:
         want = int(R * self.headroom) + 4096
         if self.capacity is None or want > self.capacity:
             self.capacity = want
+
+    def freeze(self, frozen: bool = True):
+        """Stop tracking: forwards neither copy their status words back nor record events, so a whole step (forward + backward) is a
+        fixed sequence of stream operations that torch.cuda.graph can capture and replay.  Overflows are then only visible through
+        an explicit sgr_forward_status; unfreeze to resume tracking."""
+        if frozen:
+            self.check(wait=True)
+        self.frozen = bool(frozen)
+        return self
 
     def observe_gaussians(self, n: int):
         want = int(n * self.headroom) + 1024
@@ -197,7 +207,7 @@ def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rot
     st.geom = torch.empty((gb.value,), device=device, dtype=torch.uint8)
     st.img = torch.empty((ib.value,), device=device, dtype=torch.uint8)
 
-    if capacity is not None:
+    if capacity is not None and not capacity.frozen:
         capacity.check()
     if capacity is not None and capacity.capacity is not None:
         # bounded mode: no host synchronisation anywhere in this call
@@ -211,12 +221,13 @@ def _forward_impl(means3D, sh, colors_precomp, semantics, opacities, scales, rot
                                        _ptr(semantic), _ptr(radii), _ptr(st.geom), gb.value, _ptr(st.img), ib.value, _ptr(st.binning), nbytes,
                                        cap, _stream(device))
             _capi.check(rc, "sgr_forward_bounded")
-            host_status = capacity.status_word()
-            rc = L.sgr_forward_status_async(C.byref(fr), _ptr(st.geom), C.c_void_p(host_status.data_ptr()), _stream(device))
-            _capi.check(rc, "sgr_forward_status_async")
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(device))
-        capacity.track(host_status, ev)
+            if not capacity.frozen:
+                host_status = capacity.status_word()
+                rc = L.sgr_forward_status_async(C.byref(fr), _ptr(st.geom), C.c_void_p(host_status.data_ptr()), _stream(device))
+                _capi.check(rc, "sgr_forward_status_async")
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(device))
+                capacity.track(host_status, ev)
         st.num_instances = cap
         del keep
         return color, radii, depth, alpha, semantic, st, tensors

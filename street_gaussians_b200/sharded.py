@@ -469,7 +469,8 @@ def sharded_forward_raw(settings, band, ws: "PeerWorkspace", tensors, P: int, ca
     M = int(tensors["sh"].shape[1]) if tensors["sh"] is not None else 0
     fr, keep = _make_frame(settings, P, M, 0, device, band)
     pre = 1 if ws.fwd_pending else 0
-    epoch = ws.next_epochs(1 + pre)
+    ws.next_epochs(1 + pre)  # host-side tally only: the epochs themselves are counted on the device (barrier_epoch = 0)
+    epoch = 0
     with torch.cuda.device(device):
         rc = L.sgr_sharded_forward(C.byref(fr), C.byref(ws.peers), _ptr(tensors["means3D"]), _ptr(tensors["sh"]), _ptr(tensors["colors_precomp"]),
                                    _ptr(tensors["opacities"]), _ptr(tensors["scales"]), _ptr(tensors["rotations"]), _ptr(tensors["cov3Ds_precomp"]),
@@ -502,7 +503,8 @@ def sharded_backward_raw(settings, band, ws: "PeerWorkspace", tensors, P: int, c
     g_cov = e(P, 6) if cov is not None else None
     bufs = ws.step_buffers(0)
     fr, keep = _make_frame(settings, P, M, 0, dev, band)
-    epoch = ws.next_epochs(1)
+    ws.next_epochs(1)
+    epoch = 0  # device-side count
     with torch.cuda.device(dev):
         rc = L.sgr_sharded_backward(C.byref(fr), C.byref(ws.peers), capacity, _ptr(tensors["means3D"]), _ptr(sh), _ptr(colors), _ptr(scales),
                                     _ptr(rots), _ptr(cov), _ptr(bufs["radii"]), _ptr(bufs["rec"]), _ptr(bufs["img"]), _ptr(bufs["binning"]),
@@ -521,16 +523,18 @@ def _fused_forward(ctx, tensors, settings, owner, ws: "PeerWorkspace", P: int, c
         raise _capi.SgrError("GaussianShardedRasterizer(exchange='p2p') owns ONE peer workspace: run backward() of the previous "
                              "forward (or call release_workspace()) before the next forward, or use one rasterizer per camera")
     cap = owner.capacity
-    cap.check()
+    if not cap.frozen:
+        cap.check()
     H, W = int(settings.image_height), int(settings.image_width)
     capacity = int(cap.capacity)
     # depth-order slots: learnt from the previous frames (status word 4); the first fused frame compacts into all slots
     gcap = int(cap.gaussian_capacity) if cap.gaussian_capacity is not None else ws.P_total
-    host_status = cap.status_word()
+    host_status = None if cap.frozen else cap.status_word()
     color, depth, alpha, bufs = sharded_forward_raw(settings, owner.band, ws, tensors, P, capacity, gcap, host_status)
-    ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream(device))
-    cap.track(host_status, ev)
+    if host_status is not None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        cap.track(host_status, ev)
     ws.in_flight = bool(differentiable)
     ctx.fused, ctx.settings, ctx.owner, ctx.ws, ctx.P, ctx.capacity, ctx.tensors = True, settings, owner, ws, P, capacity, tensors
     ctx.shapes = tuple(None if t is None else (tuple(t.shape), t.device, t.dtype) for t in inputs)
