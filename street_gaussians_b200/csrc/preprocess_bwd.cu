@@ -435,18 +435,41 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_tma_kernel(
 	__syncthreads();
 	const float *view = s_cam, *proj = s_cam + 16;
 	const bool visible = in_range && radius > 0;
-	if (GATHER && visible) {
-		int x0, y0, x1, y1;
-		tile_rect(q0.x, q0.y, radius, f.gx, f.gy, x0, y0, x1, y1);
-		const uint32_t mask = x1 > x0 ? touched_ranks(y0, y1, pt.world) : 0u;
+	if (GATHER) {
+		// The 12-float rows of a warp's 32 Gaussians are 1536 contiguous bytes in every rank's partial grad2d.  Read per lane they are
+		// three 16-B loads at a 48-B stride (half-used sectors, and over NVLink each a separate request); when at least half of the
+		// lanes need rank p the warp fetches the whole block with lane-contiguous 16-B loads into shared memory and each lane picks its
+		// row (rows of lanes that do not need rank p are stale there and are simply not read).
+		__shared__ float4 s_g[8][96];
+		uint32_t mask = 0u;
+		if (visible) {
+			int x0, y0, x1, y1;
+			tile_rect(q0.x, q0.y, radius, f.gx, f.gy, x0, y0, x1, y1);
+			mask = x1 > x0 ? touched_ranks(y0, y1, pt.world) : 0u;
+		}
 		const size_t g = (size_t)pt.rank * (size_t)pt.chunk + i;
+		const bool full_warp = rows == 32;
 		for (int p = 0; p < pt.world; p++) {
-			if (!((mask >> p) & 1u)) continue;
-			const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + g * 12);
-			const float4 a = src[0], b = src[1], c = src[2];
-			g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
-			g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
-			g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
+			const bool hit = (mask >> p) & 1u;
+			const unsigned hits = __ballot_sync(0xffffffffu, hit);
+			if (hits == 0u) continue;
+			float4 a, b, c;
+			if (full_warp && __popc(hits) >= 16) {
+				const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + (g - (size_t)lane) * 12);
+#pragma unroll
+				for (int k = 0; k < 3; k++) s_g[warp][k * 32 + lane] = src[k * 32 + lane];
+				__syncwarp();
+				a = s_g[warp][lane * 3]; b = s_g[warp][lane * 3 + 1]; c = s_g[warp][lane * 3 + 2];
+				__syncwarp();
+			} else if (hit) {
+				const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + g * 12);
+				a = src[0]; b = src[1]; c = src[2];
+			}
+			if (hit) {
+				g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
+				g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
+				g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
+			}
 		}
 	}
 	const float4 g0 = g0v, g1 = g1v, g2 = g2v;

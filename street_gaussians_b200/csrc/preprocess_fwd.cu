@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 	__syncthreads();
 	if (in_range) pr = project_gaussian(f, s_cam, s_cam + 16, p, shape, cov3D_precomp != nullptr);
 	if (TMA && sh_pending) mbar_wait(sh_bar, 0);  // all rows of the warp have landed (also keeps the CTA alive until they have)
+	GaussRec rec_out;
+	rec_out.q0 = rec_out.q1 = rec_out.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (in_range) {
 		if (pr.ok) {
 			float3 rgb;
@@ -275,23 +277,47 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 			r.q0 = make_float4(pr.px, pr.py, pr.conic.x, pr.conic.y);
 			r.q1 = make_float4(pr.conic.z, opacity, -0.5f * cp.qmax, pr.depth);
 			r.q2 = make_float4(rgb.x, rgb.y, rgb.z, __uint_as_float(clamp_bits));
-			rec[idx] = r;
-			if (SCATTER) {
-				const uint32_t mask = touched_ranks(pr.y0, pr.y1, pt.world);
-				const size_t g = (size_t)pt.rank * (size_t)pt.chunk + (size_t)idx;
-				for (int p = 0; p < pt.world; p++)
-					if ((mask >> p) & 1u) pt.rec[p][g] = r;
-			}
+			if (!SCATTER) rec[idx] = r;
+			else rec_out = r;
 		}
 		radii[idx] = pr.radius;
 	}
 	if (SCATTER) {
-		if ((long long)idx < pt.chunk) {
-			const uint32_t mask = pr.ok ? touched_ranks(pr.y0, pr.y1, pt.world) : 0u;
-			const size_t g = (size_t)pt.rank * (size_t)pt.chunk + (size_t)idx;
-			for (int p = 0; p < pt.world; p++) pt.radii[p][g] = ((mask >> p) & 1u) ? pr.radius : 0;
-			if (!in_range) radii[idx] = 0;  // padding slot of the local arrays
+		// The 48-B records of a warp are 1536 contiguous bytes in every destination array (global ids are consecutive).  Written as
+		// three float4 per LANE they are 32 half-filled sectors per store instruction — over NVLink that cost 152 us for 0.95 M
+		// Gaussians at N = 2 (300 GB/s, trace in profiles/r02_summary.md).  Staged through shared memory the warp writes whole 128-B
+		// lines (96 x 16 B, lane-contiguous) whenever at least half of its lanes go to that rank — the slots of the other lanes receive
+		// a record nobody reads (their radius on that rank is 0); sparse destinations (N = 8: one or two ranks per Gaussian) keep
+		// per-lane stores.
+		__shared__ float4 s_out[8][96];
+		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+		const bool slot = (long long)idx < pt.chunk;
+		const uint32_t mask = pr.ok ? touched_ranks(pr.y0, pr.y1, pt.world) : 0u;
+		const size_t g = (size_t)pt.rank * (size_t)pt.chunk + (size_t)idx;
+		s_out[warp][lane * 3] = rec_out.q0; s_out[warp][lane * 3 + 1] = rec_out.q1; s_out[warp][lane * 3 + 2] = rec_out.q2;
+		__syncwarp();
+		const bool full_warp = __all_sync(0xffffffffu, in_range);
+		const size_t g0 = g - (size_t)lane;
+		if (full_warp) {  // own copy (kept for the backward): always all 32 records
+			float4 *dst = reinterpret_cast<float4 *>(rec + (idx - lane));
+#pragma unroll
+			for (int k = 0; k < 3; k++) dst[k * 32 + lane] = s_out[warp][k * 32 + lane];
+		} else if (in_range && pr.ok) {
+			rec[idx] = rec_out;
 		}
+		for (int p = 0; p < pt.world; p++) {
+			const bool hit = (mask >> p) & 1u;
+			const unsigned hits = __ballot_sync(0xffffffffu, hit);
+			if (full_warp && __popc(hits) >= 16) {
+				float4 *dst = reinterpret_cast<float4 *>(pt.rec[p] + g0);
+#pragma unroll
+				for (int k = 0; k < 3; k++) dst[k * 32 + lane] = s_out[warp][k * 32 + lane];
+			} else if (hit) {
+				pt.rec[p][g] = rec_out;
+			}
+			if (slot) pt.radii[p][g] = hit ? pr.radius : 0;
+		}
+		if (slot && !in_range) radii[idx] = 0;  // padding slot of the local arrays
 	}
 	if (!COUNT) return;
 	uint32_t count = 0;
