@@ -183,7 +183,7 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
                         const float *cov3D_precomp, float *out_color, float *out_depth, float *out_alpha, float *out_semantic,
                         int32_t *radii, void *geom_state, size_t geom_bytes, void *img_state, size_t img_bytes, sgr_alloc_fn alloc,
                         void *alloc_user, void **binning_state, int64_t *num_instances, void *bounded_state, size_t bounded_bytes,
-                        int64_t capacity, void *stream, bool from_records = false, int64_t gaussian_capacity = -1) {
+                        int64_t capacity, void *stream, bool from_records = false) {
 	FrameDev f;
 	int rc = make_frame(frame, f);
 	if (rc) return rc;
@@ -226,7 +226,7 @@ static int forward_impl(const SgrFrame *frame, const float *means3D, const float
 		else
 			SGR_TRY(launch_preprocess_fwd(f, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii, g, st),
 			        "preprocess_fwd");
-		SGR_TRY(launch_depth_order(f, g, st, bounded ? gaussian_capacity : -1, &n_order), "depth_order");
+		SGR_TRY(launch_depth_order(f, g, st), "depth_order");
 		if (!bounded) {
 			uint32_t r32 = 0;
 			cudaError_t e = read_back_u32(&r32, g.offsets + (n_order - 1), st);
@@ -421,10 +421,13 @@ int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const floa
 	SGR_TRY(cudaMemsetAsync(g.big_count, 0, 64 * sizeof(uint32_t), st), "status reset");
 	SGR_TRY(launch_peer_barrier(pt, barrier_epoch, g.big_count, st), "barrier");
 	int n_order = ft.P;
-	SGR_TRY(launch_count_tiles(ft, g, pt.radii[pt.rank], st, const_cast<float *>(pt.grad2d[pt.rank])), "count_tiles");
-	SGR_TRY(launch_depth_order(ft, g, st, gaussian_capacity, &n_order), "depth_order");
+	SGR_TRY(launch_count_and_order(ft, g, pt.radii[pt.rank], st, gaussian_capacity, const_cast<float *>(pt.grad2d[pt.rank]), &n_order), "count + depth_order");
 	const BinView b = capacity > 0 ? carve_bin(binning_state, capacity) : carve_bin(nullptr, 0);
 	SGR_TRY(launch_binning(ft, g, pt.radii[pt.rank], b, img, capacity, st, capacity, n_order), "binning");
+	// the delivered radii have been consumed (count, emit): clear them for the next frame's owners, who only store to the ranks they
+	// deliver to.  No peer writes this array before it has passed a barrier this rank reaches after this memset (the backward's,
+	// or the leading barrier of a forward that follows a forward).
+	SGR_TRY(cudaMemsetAsync(pt.radii[pt.rank], 0, (size_t)ft.P * sizeof(int32_t), st), "radii reset");
 	SGR_TRY(launch_blend_fwd(ft, g, b, img, nullptr, out_color, out_depth, out_alpha, nullptr, st), "blend_fwd");
 	return SGR_OK;
 }

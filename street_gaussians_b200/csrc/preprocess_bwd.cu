@@ -449,26 +449,46 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_tma_kernel(
 		}
 		const size_t g = (size_t)pt.rank * (size_t)pt.chunk + i;
 		const bool full_warp = rows == 32;
+		// dense destinations first (block fetch through shared memory), remembering which peers are left for this lane
+		uint32_t left = mask;
 		for (int p = 0; p < pt.world; p++) {
 			const bool hit = (mask >> p) & 1u;
 			const unsigned hits = __ballot_sync(0xffffffffu, hit);
-			if (hits == 0u) continue;
-			float4 a, b, c;
-			if (full_warp && __popc(hits) >= 16) {
-				const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + (g - (size_t)lane) * 12);
+			if (!(full_warp && __popc(hits) >= 16)) continue;
+			const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + (g - (size_t)lane) * 12);
 #pragma unroll
-				for (int k = 0; k < 3; k++) s_g[warp][k * 32 + lane] = src[k * 32 + lane];
-				__syncwarp();
-				a = s_g[warp][lane * 3]; b = s_g[warp][lane * 3 + 1]; c = s_g[warp][lane * 3 + 2];
-				__syncwarp();
-			} else if (hit) {
-				const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + g * 12);
-				a = src[0]; b = src[1]; c = src[2];
-			}
+			for (int k = 0; k < 3; k++) s_g[warp][k * 32 + lane] = src[k * 32 + lane];
+			__syncwarp();
 			if (hit) {
+				const float4 a = s_g[warp][lane * 3], b = s_g[warp][lane * 3 + 1], c = s_g[warp][lane * 3 + 2];
 				g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
 				g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
 				g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
+				left &= ~(1u << p);
+			}
+			__syncwarp();
+		}
+		// sparse destinations (the N = 8 case: one or two ranks per Gaussian): the rows of up to three peers are requested TOGETHER and
+		// summed in ascending rank order afterwards — one NVLink round trip instead of one per peer (94 us -> see profiles/r02_summary.md)
+		while (left != 0u) {
+			int pp[3];
+			float4 v[3][3];
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				pp[k] = left ? __ffs(left) - 1 : -1;
+				if (pp[k] >= 0) {
+					left &= left - 1u;
+					const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[pp[k]] + g * 12);
+					v[k][0] = src[0]; v[k][1] = src[1]; v[k][2] = src[2];
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				if (pp[k] >= 0) {
+					g0v.x += v[k][0].x; g0v.y += v[k][0].y; g0v.z += v[k][0].z; g0v.w += v[k][0].w;
+					g1v.x += v[k][1].x; g1v.y += v[k][1].y; g1v.z += v[k][1].z; g1v.w += v[k][1].w;
+					g2v.x += v[k][2].x; g2v.y += v[k][2].y; g2v.z += v[k][2].z; g2v.w += v[k][2].w;
+				}
 			}
 		}
 	}

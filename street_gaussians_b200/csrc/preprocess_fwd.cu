@@ -305,17 +305,28 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		} else if (in_range && pr.ok) {
 			rec[idx] = rec_out;
 		}
+		// Radii go ONLY to the ranks that receive the record: every rank clears its radii_all after it has binned a frame
+		// (sgr_sharded_forward), so "not delivered" is the zero that is already there.  The round-2 first cut stored a radius
+		// (mostly 0) to all N ranks: 8 remote 128-B lines per warp at N = 8, 103 us for 237 k Gaussians (profiles/r02_summary.md).
 		for (int p = 0; p < pt.world; p++) {
 			const bool hit = (mask >> p) & 1u;
 			const unsigned hits = __ballot_sync(0xffffffffu, hit);
-			if (full_warp && __popc(hits) >= 16) {
+			if (hits == 0u) continue;
+			const int n_hit = __popc(hits);
+			if (full_warp && n_hit >= 16) {
 				float4 *dst = reinterpret_cast<float4 *>(pt.rec[p] + g0);
 #pragma unroll
 				for (int k = 0; k < 3; k++) dst[k * 32 + lane] = s_out[warp][k * 32 + lane];
-			} else if (hit) {
-				pt.rec[p][g] = rec_out;
+			} else {
+				// sparse destination: piece e = 3 * (rank of the record among the hit lanes) + (16-B third of it); consecutive lanes
+				// write consecutive thirds, so a record leaves as ONE 48-B run instead of three half-filled sectors in three stores
+				for (int e = lane; e < 3 * n_hit; e += 32) {
+					const int which = e / 3, piece = e - 3 * which;
+					const int src_lane = __fns(hits, 0, which + 1);
+					reinterpret_cast<float4 *>(pt.rec[p] + g0 + src_lane)[piece] = s_out[warp][src_lane * 3 + piece];
+				}
 			}
-			if (slot) pt.radii[p][g] = hit ? pr.radius : 0;
+			if (hit) pt.radii[p][g] = pr.radius;
 		}
 		if (slot && !in_range) radii[idx] = 0;  // padding slot of the local arrays
 	}

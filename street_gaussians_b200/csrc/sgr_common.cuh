@@ -210,7 +210,8 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
 cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
-cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st, int64_t cap_v = -1, int *n_order = nullptr);
+cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
+cudaError_t launch_count_and_order(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st, int64_t cap_v, float *zero_rows, int *n_order);
 // Gaussian-sharded exchange over peer memory (peer_exchange.cu); device copy of include/sgr.h's SgrPeers
 constexpr int kMaxPeers = 16;
 struct PeerTable {

@@ -250,6 +250,7 @@ class PeerWorkspace:
             import torch.distributed._symmetric_memory as symm
             self.buf = symm.empty(self.total, dtype=torch.uint8, device=device)
             self.buf[self.off_flags:].zero_()  # barrier pads start at epoch 0
+            self.buf[self.off_radii: self.off_grad].zero_()  # sgr_sharded_forward's invariant: radii_all is all zero on entry
             self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
             ptrs = list(self.hdl.buffer_ptrs)
             self.hdl.barrier(channel=0)  # every pad is zero before any rank can send its first epoch
@@ -258,6 +259,8 @@ class PeerWorkspace:
         self.grad2d = self.buf[self.off_grad: self.off_grad + 48 * self.P_total].view(torch.float32).view(self.P_total, 12)
         if _buffers is not None:
             self.buf[self.off_flags:].zero_()
+            self.buf[self.off_radii: self.off_grad].zero_()
+        self.radii_dirty = False  # a staged frame (sgr_scatter_records) has written every radius slot since the last fused frame
         self.peers = _capi.SgrPeers()
         self.peers.world, self.peers.rank, self.peers.chunk = self.world, self.rank, self.chunk
         for p in range(self.world):
@@ -372,6 +375,7 @@ class _GaussianShardedRasterize(torch.autograd.Function):
             scatter_records(settings, ws, rec, radii, P)
             ws.barrier()
             ws.fwd_pending = True
+            ws.radii_dirty = True
             st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
         else:
             st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
@@ -525,6 +529,12 @@ def _fused_forward(ctx, tensors, settings, owner, ws: "PeerWorkspace", P: int, c
     cap = owner.capacity
     if not cap.frozen:
         cap.check()
+    if ws.radii_dirty:  # the staged path wrote every slot of radii_all; the fused path expects zeros (include/sgr.h)
+        if ws.fwd_pending:
+            ws.barrier()
+        ws.radii_all.zero_()
+        ws.barrier()
+        ws.radii_dirty, ws.fwd_pending = False, False
     H, W = int(settings.image_height), int(settings.image_width)
     capacity = int(cap.capacity)
     # depth-order slots: learnt from the previous frames (status word 4); the first fused frame compacts into all slots

@@ -409,7 +409,8 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
     st0 = util.settings_from(sgb, frames[0]["cam"], dev)
     wss = SH.PeerWorkspace.emulate(st0, chunk, world, dev)
     for ws in wss:
-        ws.buf[: ws.off_flags].fill_(0x7f)  # poison everything but the barrier pads
+        ws.buf[: ws.off_flags].fill_(0x7f)  # poison everything but the barrier pads ...
+        ws.radii_all.zero_()                # ... and radii_all, which the fused forward requires to be zero on entry (include/sgr.h)
     streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
     for fi, scene in enumerate(frames):
         st = util.settings_from(sgb, scene["cam"], dev)
@@ -448,17 +449,15 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
                 imgs = [sum(o[i] for o in outs) for i in range(3)]
                 for a, b, name in zip(imgs, (col, dep, alp), ("color", "depth", "alpha")):
                     assert torch.equal(a, b), f"{tag}: {name} differs from the single-GPU render"
-                if compact:
-                    assert n_sel_total < 0.8 * world * int((rad > 0).sum())  # each band sorts its own Gaussians, not all of them
+                if compact:  # each band counts / sorts the Gaussians delivered to it, not all of them
+                    assert n_sel_total <= world * int((rad > 0).sum()) and (world < 4 or n_sel_total < 0.8 * world * int((rad > 0).sum()))
                 grads = []
                 for r in range(world):
                     with torch.cuda.stream(streams[r]):
                         grads.append(SH.sharded_backward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], int(local[r]["means3D"].shape[0]),
                                                              capacity, outs[r][2], t["grad_color"], t["grad_depth"], t["grad_alpha"]))
                 torch.cuda.synchronize()
-                # the partial sums every rank left in its workspace add up to the single-GPU grad2d (rows a rank never received are stale)
-                part = sum(torch.where((ws.radii_all[:P] > 0)[:, None], ws.grad2d[:P], torch.zeros_like(ws.grad2d[:P])).double() for ws in wss)
-                assert util.rel_err(part.cpu().numpy(), g2d.double().cpu().numpy()) < 1e-5, f"{tag}: partial grad2d sums"
+                assert all(int(ws.radii_all.abs().sum()) == 0 for ws in wss), f"{tag}: radii_all must be left zeroed for the next frame"
                 for i, ref in enumerate(ref_grads):
                     if ref is None:
                         assert all(g[i] is None for g in grads)
