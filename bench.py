@@ -241,7 +241,7 @@ def rank_models(raw, lo, hi, dev):
     return models, actors
 
 
-def composed_e2e(args, mod, rast, scene, cam, dev, lo, hi, means2D, upstream, ref_cuda, barrier, use_dist, n_e2e):
+def composed_e2e(args, mod, rast, scene, cam, dev, lo, hi, means2D, upstream, ref_cuda, barrier, use_dist, n_e2e, capacity=None):
     """frames/s of  compose -> rasterize -> backward  with the raw parameters resident on the device and the per-frame inputs
     (view / projection matrix, camera centre, actor poses) copied from PINNED HOST memory inside the timed region; the scalar loss is
     read back.  Reference arm: the reference's own compose math as the PyTorch ops it is (oracle/compose_oracle.py restates
@@ -291,13 +291,53 @@ def composed_e2e(args, mod, rast, scene, cam, dev, lo, hi, means2D, upstream, re
     for i in range(3):
         frame(i % 2)
     barrier()
+    # The whole frame — pinned-host -> device copies of the camera and poses, compose, rasterize, loss, backward through both, loss ->
+    # pinned host — as ONE CUDA graph (the copies are graph nodes: every replay re-reads the pinned buffers, which is where a trainer
+    # writes the next frame's camera / poses).  Falls back to the eager loop when capture is impossible, like the main timed region.
+    graph, graph_note = None, None
+    if (not ref_cuda and args.graph != "off" and capacity is not None and capacity.capacity is not None
+            and (not use_dist or args.mp_mode == "gaussian-p2p")):
+        try:
+            capacity.freeze()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    frame(0)
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                frame(0)
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            graph, graph_note = None, f"capture failed, eager loop timed instead: {e!r}"[:300]
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+        if use_dist:
+            flag = torch.tensor([1 if graph is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                graph, graph_note = None, graph_note or "capture failed on another rank; eager loop timed instead"
+        if graph is None:
+            capacity.freeze(False)
+            frame(0)
+        barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(n_e2e):
-        frame(i % 2)
+        if graph is not None:
+            graph.replay()
+        else:
+            frame(i % 2)
     b.record()
     barrier()
     _ = float(loss_host.item())
+    timed_graph = graph is not None
     ms = a.elapsed_time(b) / n_e2e
     if use_dist:
         t = torch.tensor([ms], device=dev)
@@ -308,7 +348,12 @@ def composed_e2e(args, mod, rast, scene, cam, dev, lo, hi, means2D, upstream, re
         h2d = int(t.item())
     if old_settings is not None and not ref_cuda:
         rast.raster_settings = old_settings
+    if graph is not None:
+        capacity.freeze(False)
+        del graph
     return dict(value=1000.0 / ms, unit="frames/s", ms_per_step=ms, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+                timed_region=("CUDA graph of the whole frame (H2D copies, compose, rasterize, loss, backward, D2H loss), replayed %d times" % n_e2e)
+                if timed_graph else ("eager Python loop" + (" (%s)" % graph_note if graph_note else "")),
                 note=("compose (sgr_compose_*) -> rasterize -> backward through both; raw per-model parameters resident in HBM; camera matrices + "
                       "%d actor poses copied from pinned host memory every step; scalar loss read back" % n_act) if not ref_cuda else
                      ("reference compose math as PyTorch ops -> unmodified reference rasterizer -> autograd backward; same residency and "
@@ -724,7 +769,8 @@ def main():
     # a training run; what a frame brings from the host is the camera and the tracked actor poses ----
     e2e_comp = None
     if "raw" in scene:
-        e2e_comp = composed_e2e(args, mod, rast, scene, cam, dev, lo, hi, means2D, (gc, gd, ga), ref_cuda, barrier, use_dist, n_e2e)
+        e2e_comp = composed_e2e(args, mod, rast, scene, cam, dev, lo, hi, means2D, (gc, gd, ga), ref_cuda, barrier, use_dist, n_e2e,
+                                capacity=None if ref_cuda else capacity)
     if sampler:
         sampler.mark(1)
     clocks = sampler.stop() if sampler else None
