@@ -159,27 +159,28 @@ def test_instance_capacity_bookkeeping():
 
 
 def test_header_compiles_as_c_and_struct_layouts_match_ctypes(tmp_path):
-    """include/sgr.h is a plain-C header (no C++, no torch types) and the ctypes mirrors in _capi.py have the same size and
-    field offsets as the C structs — the boundary a cgo / JNI / ctypes binding would be written against."""
+    """include/sgr.h is a plain-C header (no C++, no torch types) and EVERY ctypes mirror in _capi.py has the same size and
+    field offsets as its C struct — the boundary a cgo / JNI / ctypes binding would be written against."""
     import subprocess
     src = tmp_path / "layout.c"
-    fields_frame = [f[0] for f in _capi.SgrFrame._fields_]
-    fields_peers = [f[0] for f in _capi.SgrPeers._fields_]
-    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "sgr.h"', 'int main(void) {',
-            '  printf("SgrFrame %zu\\n", sizeof(SgrFrame));', '  printf("SgrPeers %zu\\n", sizeof(SgrPeers));']
-    body += [f'  printf("SgrFrame.{f} %zu\\n", offsetof(SgrFrame, {f}));' for f in fields_frame]
-    body += [f'  printf("SgrPeers.{f} %zu\\n", offsetof(SgrPeers, {f}));' for f in fields_peers]
-    body += ['  printf("SGR_MAX_PEERS %d\\n", SGR_MAX_PEERS);', '  printf("SGR_ABI_VERSION %d\\n", SGR_ABI_VERSION);', '  return 0;', '}']
+    structs = ["SgrFrame", "SgrPeers", "SgrSegment", "SgrSegmentGrads", "SgrStatSegment", "SgrAdamTensor"]
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "sgr.h"', 'int main(void) {']
+    for name in structs:
+        body.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        body += [f'  printf("{name}.{f[0]} %zu\\n", offsetof({name}, {f[0]}));' for f in getattr(_capi, name)._fields_]
+    body += ['  printf("SGR_MAX_PEERS %d\\n", SGR_MAX_PEERS);', '  printf("SGR_ABI_VERSION %d\\n", SGR_ABI_VERSION);',
+             '  printf("SGR_MAX_FOURIER %d\\n", SGR_MAX_FOURIER);', '  return 0;', '}']
     src.write_text("\n".join(body))
     exe = tmp_path / "layout"
     subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
-    assert int(out["SgrFrame"]) == C.sizeof(_capi.SgrFrame) and int(out["SgrPeers"]) == C.sizeof(_capi.SgrPeers)
-    for f in fields_frame:
-        assert int(out[f"SgrFrame.{f}"]) == getattr(_capi.SgrFrame, f).offset, f
-    for f in fields_peers:
-        assert int(out[f"SgrPeers.{f}"]) == getattr(_capi.SgrPeers, f).offset, f
+    for name in structs:
+        ct = getattr(_capi, name)
+        assert int(out[name]) == C.sizeof(ct), name
+        for f in ct._fields_:
+            assert int(out[f"{name}.{f[0]}"]) == getattr(ct, f[0]).offset, (name, f[0])
     assert int(out["SGR_MAX_PEERS"]) == _capi.MAX_PEERS and int(out["SGR_ABI_VERSION"]) == _capi.ABI_VERSION
+    assert int(out["SGR_MAX_FOURIER"]) == _capi.MAX_FOURIER
 
 
 def test_gaussian_sharded_entry_points_validate_before_touching_cuda():

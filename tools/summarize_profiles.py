@@ -72,10 +72,17 @@ with open(os.path.join(out_dir, f"{tag}_ncu_full.md"), "w") as f:
 # 3. profiles/ncu_traffic.json: what bench.py's roofline.traffic / issue_active_pct read — keyed by kernel, valid only for the workload
 #    it was captured on and for the exact version of the kernel's source file (sha256 prefix)
 import hashlib, json
-SRC = {"blend_bwd2_kernel": "blend_bwd2.cu", "blend_fwd_kernel": "blend_fwd.cu", "preprocess_fwd_kernel": "preprocess_fwd.cu",
-       "preprocess_bwd_tma_kernel": "preprocess_bwd.cu", "preprocess_bwd_kernel": "preprocess_bwd.cu", "compose_fwd_kernel": "compose.cu",
-       "compose_bwd_kernel": "compose.cu", "emit_pairs_kernel": "binning.cu", "emit_big_kernel": "binning.cu", "tile_ranges_kernel": "binning.cu",
-       "count_tiles_kernel": "binning.cu"}
+# (substring of the demangled kernel name, key in ncu_traffic.json, source file) — first match wins
+PATTERNS = [("preprocess_fwd_kernel<0, 1", "preprocess_fwd_scatter_kernel", "preprocess_fwd.cu"),
+            ("preprocess_bwd_tma_kernel<1>", "preprocess_bwd_gather_kernel", "preprocess_bwd.cu"),
+            ("blend_bwd2_kernel", "blend_bwd2_kernel", "blend_bwd2.cu"), ("blend_fwd_kernel", "blend_fwd_kernel", "blend_fwd.cu"),
+            ("preprocess_fwd_kernel", "preprocess_fwd_kernel", "preprocess_fwd.cu"),
+            ("preprocess_bwd_tma_kernel", "preprocess_bwd_tma_kernel", "preprocess_bwd.cu"),
+            ("preprocess_bwd_kernel", "preprocess_bwd_kernel", "preprocess_bwd.cu"),
+            ("compose_fwd_kernel", "compose_fwd_kernel", "compose.cu"), ("compose_bwd_kernel", "compose_bwd_kernel", "compose.cu"),
+            ("emit_pairs_kernel", "emit_pairs_kernel", "binning.cu"), ("emit_big_kernel", "emit_big_kernel", "binning.cu"),
+            ("tile_ranges_kernel", "tile_ranges_kernel", "binning.cu"), ("count_compact_kernel", "count_compact_kernel", "binning.cu"),
+            ("count_tiles_kernel", "count_tiles_kernel", "binning.cu")]
 traffic_path = os.path.join(out_dir, "ncu_traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 workload = os.environ.get("SGR_PROFILE_WORKLOAD", "C")
@@ -89,12 +96,13 @@ for rep in reps:
     units = rows[1]
     for r in rows[2:]:
         name = r[ix["Kernel Name"]]
-        key = next((k for k in sorted(SRC, key=len, reverse=True) if k in name), None)
-        if key is None or "dram__bytes_read.sum" not in ix:
+        hit = next(((k, src) for pat, k, src in PATTERNS if pat in name), None)
+        if hit is None or "dram__bytes_read.sum" not in ix:
             continue
+        key, src_file = hit
         rd = float(r[ix["dram__bytes_read.sum"]]) * conv.get(units[ix["dram__bytes_read.sum"]], 1.0)
         wr = float(r[ix["dram__bytes_write.sum"]]) * conv.get(units[ix["dram__bytes_write.sum"]], 1.0)
-        sha = hashlib.sha256(open(os.path.join(ROOT, "street_gaussians_b200", "csrc", SRC[key]), "rb").read()).hexdigest()[:16]
+        sha = hashlib.sha256(open(os.path.join(ROOT, "street_gaussians_b200", "csrc", src_file), "rb").read()).hexdigest()[:16]
         traffic[key] = dict(workload=workload, source_sha16=sha, dram_bytes=rd + wr, dram_bytes_read=rd, dram_bytes_write=wr,
                             time_us=float(r[ix["gpu__time_duration.sum"]]) * (1e-3 if units[ix["gpu__time_duration.sum"]] in ("ns", "nsecond") else 1.0),
                             issue_active_pct=float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]), capture=os.path.basename(rep),
