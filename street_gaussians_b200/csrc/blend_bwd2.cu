@@ -23,15 +23,18 @@
 
 namespace sgr {
 
-constexpr int kB2 = 32;  // splats per batch
 constexpr uint32_t kRec2 = 48;
-constexpr uint32_t kOffWQ = 0;                            // float2 [kB2][256]
-constexpr uint32_t kOffPix = kB2 * 256 * 8;               // float4 [256]   dL/dpixel rgb, dL/dpixel depth
-constexpr uint32_t kOffPxy = kOffPix + 256 * 16;          // float2 [256]   pixel centre
-constexpr uint32_t kOffRec = kOffPxy + 256 * 8;           // [2][kB2 * 48]  staged GaussRec
-constexpr uint32_t kOffId = kOffRec + 2 * kB2 * kRec2;    // u32 [2][kB2]
-constexpr uint32_t kOffMask = kOffId + 2 * kB2 * 4;       // u32 [8]        per-warp "slot has contributions" bits
-constexpr uint32_t kSmem2 = kOffMask + 8 * 4;
+// shared-memory map of one CTA for a batch of B splats (B = 32: 75 KB, 3 CTAs/SM; B = 16: 40 KB, 4 CTAs/SM at 64 registers)
+template <int B>
+struct Smem2 {
+	static constexpr uint32_t kOffWQ = 0;                          // float2 [B][256]
+	static constexpr uint32_t kOffPix = B * 256 * 8;               // float4 [256]   dL/dpixel rgb, dL/dpixel depth
+	static constexpr uint32_t kOffPxy = kOffPix + 256 * 16;        // float2 [256]   pixel centre
+	static constexpr uint32_t kOffRec = kOffPxy + 256 * 8;         // [2][B * 48]    staged GaussRec
+	static constexpr uint32_t kOffId = kOffRec + 2 * B * kRec2;    // u32 [2][B]
+	static constexpr uint32_t kOffMask = kOffId + 2 * B * 4;       // u32 [8]        per-warp "slot has contributions" bits
+	static constexpr uint32_t kBytes = kOffMask + 8 * 4;
+};
 
 __device__ __forceinline__ float4 ld4(uint32_t a) {
 	float4 v;
@@ -54,13 +57,18 @@ __device__ __forceinline__ void st4(uint32_t a, float4 v) {
 __device__ __forceinline__ void st2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
 __device__ __forceinline__ void stu(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-__global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
+template <int kB2, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
                                                          const uint32_t *__restrict__ point_list, const GaussRec *__restrict__ rec,
                                                          const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tile_max_contrib,
                                                          const float *__restrict__ alphas, const float *__restrict__ dL_dpixels,
                                                          const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dalphas,
                                                          float *__restrict__ grad2d) {
 	extern __shared__ __align__(16) unsigned char smem2[];
+	using L = Smem2<kB2>;
+	constexpr uint32_t kOffWQ = L::kOffWQ, kOffPix = L::kOffPix, kOffPxy = L::kOffPxy, kOffRec = L::kOffRec, kOffId = L::kOffId, kOffMask = L::kOffMask;
+	constexpr int kTPS = 256 / kB2;  // phase-2 threads per splat (8 or 16: consecutive lanes)
+	constexpr int kPPC = 256 / kTPS; // pixels per phase-2 thread (32 or 16)
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int tile_x = blockIdx.x, tile_y = f.band.begin + blockIdx.y * f.band.step;
 	const int tile = tile_y * f.gx + tile_x;
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 	stash(0);
 
 	// phase-2 role of this thread
-	const int p2_slot = tid >> 3, p2_chunk = tid & 7;
+	const int p2_slot = tid / kTPS, p2_chunk = tid % kTPS;
 
 	for (int b = 0; b < nb; b++) {
 		__syncthreads();  // record buffer b&1 published; phase 2 of the previous batch is done with s_wq / s_mask
@@ -180,17 +188,17 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 		// ---------------- phase 2: per-splat sums over the tile's pixels ----------------
 		{
 			float Sq = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sabs = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
-			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (uint32_t)p2_chunk * 4u) >> p2_slot) & 1u);
+			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (uint32_t)(p2_chunk * kPPC / 32) * 4u) >> p2_slot) & 1u);
 			float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
 			if (live) {
 				r0 = ld4(rbase + (uint32_t)p2_slot * kRec2);
 				r1 = ld4(rbase + (uint32_t)p2_slot * kRec2 + 16);
-				const uint32_t row = sb + kOffWQ + (uint32_t)(p2_slot * 256 + p2_chunk * 32) * 8u;
-				const uint32_t pixb = sb + kOffPix + (uint32_t)(p2_chunk * 32) * 16u;
-				const uint32_t pxyb = sb + kOffPxy + (uint32_t)(p2_chunk * 32) * 8u;
+				const uint32_t row = sb + kOffWQ + (uint32_t)(p2_slot * 256 + p2_chunk * kPPC) * 8u;
+				const uint32_t pixb = sb + kOffPix + (uint32_t)(p2_chunk * kPPC) * 16u;
+				const uint32_t pxyb = sb + kOffPxy + (uint32_t)(p2_chunk * kPPC) * 8u;
 #pragma unroll 4
-				for (int i = 0; i < 32; i++) {
-					const uint32_t l = (uint32_t)(i + lane) & 31u;  // bank rotation: the 32 lanes of a warp hit 32 distinct pixels
+				for (int i = 0; i < kPPC; i++) {
+					const uint32_t l = (uint32_t)(i + lane) & (uint32_t)(kPPC - 1);  // bank rotation: the lanes of a (half-)warp hit distinct pixels
 					const float2 wq = ld2(row + l * 8u);
 					const float4 pg = ld4(pixb + l * 16u);
 					const float2 pc = ld2(pxyb + l * 8u);
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 			const unsigned any_live = __ballot_sync(0xffffffffu, live);
 			if (any_live) {
 #pragma unroll
-				for (int o = 1; o < 8; o <<= 1) {
+				for (int o = 1; o < kTPS; o <<= 1) {
 					Sq += __shfl_xor_sync(0xffffffffu, Sq, o); Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
 					Sy += __shfl_xor_sync(0xffffffffu, Sy, o); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
 					Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o); Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
@@ -221,28 +229,37 @@ __global__ void __launch_bounds__(256) blend_bwd2_kernel(const FrameDev f, const
 					Cg += __shfl_xor_sync(0xffffffffu, Cg, o); Cb += __shfl_xor_sync(0xffffffffu, Cb, o);
 					Cd += __shfl_xor_sync(0xffffffffu, Cd, o);
 				}
-				// is any chunk of this splat live?  (bits of the 8 lanes of this slot in the ballot)
-				const unsigned grp = (any_live >> (lane & 24)) & 0xffu;
+				// is any chunk of this splat live?  (bits of the kTPS lanes of this slot in the ballot)
+				const int g0 = lane & ~(kTPS - 1);
+				const unsigned grp = (any_live >> g0) & ((1u << kTPS) - 1u);
 				// the conic / opacity of the splat: lanes that were not live did not load the record (all lanes shuffle)
-				const int srcl = grp != 0u ? (lane & 24) + (__ffs(grp) - 1) : lane;
+				const int srcl = grp != 0u ? g0 + (__ffs(grp) - 1) : lane;
 				const float ca = __shfl_sync(0xffffffffu, r0.z, srcl), cb = __shfl_sync(0xffffffffu, r0.w, srcl);
 				const float cc = __shfl_sync(0xffffffffu, r1.x, srcl), op = __shfl_sync(0xffffffffu, r1.y, srcl);
 				if (grp != 0u && p2_slot < cnt) {
 					const uint32_t gid = ldu(sb + kOffId + (uint32_t)(buf * kB2 + p2_slot) * 4u);
 					float *dst = grad2d + (size_t)gid * 12;
-					float o0, o1 = 0.f;
-					switch (p2_chunk) {  // lane c of the group writes components c and c + 8
-						case 0: o0 = -kW * (ca * Sx + cb * Sy); o1 = Cg; break;
-						case 1: o0 = -kH * (cc * Sy + cb * Sx); o1 = Cb; break;
-						case 2: o0 = Sabs; o1 = Cd; break;
-						case 3: o0 = -0.5f * Sxx; break;
-						case 4: o0 = -0.5f * Sxy; break;
-						case 5: o0 = -0.5f * Syy; break;
-						case 6: o0 = (op != 0.f) ? Sq / op : 0.f; break;
-						default: o0 = Cr; break;
+					auto comp = [&](int k) -> float {  // component k of the grad2d row
+						switch (k) {
+							case 0: return -kW * (ca * Sx + cb * Sy);
+							case 1: return -kH * (cc * Sy + cb * Sx);
+							case 2: return Sabs;
+							case 3: return -0.5f * Sxx;
+							case 4: return -0.5f * Sxy;
+							case 5: return -0.5f * Syy;
+							case 6: return (op != 0.f) ? Sq / op : 0.f;
+							case 7: return Cr;
+							case 8: return Cg;
+							case 9: return Cb;
+							default: return Cd;
+						}
+					};
+					if (kTPS == 8) {  // lane c of the group writes components c and (c < 3) c + 8
+						atomicAdd(dst + p2_chunk, comp(p2_chunk));
+						if (p2_chunk < 3) atomicAdd(dst + 8 + p2_chunk, comp(8 + p2_chunk));
+					} else if (p2_chunk < 11) {
+						atomicAdd(dst + p2_chunk, comp(p2_chunk));
 					}
-					atomicAdd(dst + p2_chunk, o0);
-					if (p2_chunk < 3) atomicAdd(dst + 8 + p2_chunk, o1);
 				}
 			}
 		}
@@ -258,11 +275,23 @@ cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView 
 	if (e != cudaSuccess) return e;
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
-	static std::atomic<uint64_t> configured{0};
-	if ((e = ensure_dynamic_smem(blend_bwd2_kernel, (int)kSmem2, configured)) != cudaSuccess) return e;
+	// batch size: 32 splats (75 KB of shared memory, 3 CTAs/SM) unless SGR_BWD2_BATCH=16 (40 KB, 4 CTAs/SM) — A/B'd in round 2
+	//             SGR_BWD2_BATCH=165: 16 splats with the register budget of 5 CTAs/SM
+	static const int batch = [] { const char *e = getenv("SGR_BWD2_BATCH"); const int v = e ? atoi(e) : 32; return (v == 16 || v == 165 || v == 323) ? v : 32; }();
+	static std::atomic<uint64_t> configured32{0}, configured16{0}, configured165{0}, configured323{0};
 	count_launch();
-	blend_bwd2_kernel<<<dim3(f.gx, rows), 256, kSmem2, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, img.tile_max_contrib, out_alpha,
-	                                                         dL_dcolor, dL_ddepth, dL_dalpha, grad2d);
+#define SGR_LAUNCH_BWD2(B, C, FLAG)                                                                                                         \
+	do {                                                                                                                                    \
+		if ((e = ensure_dynamic_smem(blend_bwd2_kernel<B, C>, (int)Smem2<B>::kBytes, FLAG)) != cudaSuccess) return e;                       \
+		blend_bwd2_kernel<B, C><<<dim3(f.gx, rows), 256, Smem2<B>::kBytes, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib,            \
+		                                                                        img.tile_max_contrib, out_alpha, dL_dcolor, dL_ddepth,       \
+		                                                                        dL_dalpha, grad2d);                                          \
+	} while (0)
+	if (batch == 16) SGR_LAUNCH_BWD2(16, 4, configured16);
+	else if (batch == 165) SGR_LAUNCH_BWD2(16, 5, configured165);
+	else if (batch == 323) SGR_LAUNCH_BWD2(32, 3, configured323);  // 32 splats, up to 85 registers
+	else SGR_LAUNCH_BWD2(32, 4, configured32);                     // 32 splats, 64 registers (3 CTAs/SM by shared memory)
+#undef SGR_LAUNCH_BWD2
 	return cudaGetLastError();
 }
 
