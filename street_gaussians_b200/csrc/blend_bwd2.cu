@@ -19,6 +19,9 @@
 // matrix and triple-buffered records, so that phase 2 of batch b overlaps phase 1 of batch b+1.  The shared-memory budget forces
 // 16-splat batches (2 x 32 KB), i.e. 16 phase-2 threads per splat, a 4-step butterfly and twice the per-splat fixed cost:
 // 677 us vs 618 us for this kernel; 8-splat batches (4 CTAs/SM) 775 us; 32-splat double-buffered (1 CTA/SM) 1138 us.
+// Also measured (same kernel, SGR_BWD2_BATCH): 16-splat batches at 4 CTAs/SM 640 us, at 5 CTAs/SM (48 registers, 16 B spilled) 718 us,
+// 32-splat batches with 79 registers 615 us, vs 613 us for the default (32 splats, 63 registers, 3 CTAs/SM).  More resident warps buy
+// nothing: the kernel is bound by the NUMBER of instructions it issues (76 % issue-active), not by latency.
 #include "sgr_common.cuh"
 
 namespace sgr {
