@@ -220,18 +220,24 @@ int sgr_gather_grad2d(const SgrFrame *frame, const SgrPeers *peers, const void *
 int sgr_peer_barrier(const SgrPeers *peers, uint32_t epoch, void *stream);
 
 /* The Gaussian-sharded forward as ONE call (steps 1-3 above with the peer-memory exchange): project the rank's frame.P Gaussians and
- * store every record straight into the gathered arrays of the ranks whose band it meets (one kernel), device barrier, then bin /
- * sort / blend the rank's band from its gathered records — ~28 kernel launches issued back to back from C instead of six
- * Python-level calls (the N = 8 step was host-launch bound: profiles/r01_bench_n8_gaussian_p2p_diag.txt).
+ * deliver their records to the ranks whose band they meet (one kernel), device barrier, then bin / sort / blend the rank's band from
+ * the delivered records — all launches issued back to back from C instead of six Python-level calls (the N = 8 step was host-launch
+ * bound: profiles/r01_bench_n8_gaussian_p2p_diag.txt).
+ *   Delivery is by BLOCK RUNS, not by global index: the 256 consecutive Gaussians [256 b, 256 b + 256) of owner s that rank d needs
+ *   are stored as one contiguous run into the first slots of [s*chunk + 256 b, +256) of rank d's record array (whole 128-B lines over
+ *   NVLink), with the radius packed into the record; run lengths go to a table inside rank d's geom_state.  Ascending slot order
+ *   equals ascending global-id order, so the depth order (ties included) and every pixel equal the single-GPU render.  In this mode
+ *   peers->radii[rank] and the rows of peers->grad2d[rank] are indexed by SLOT; sgr_sharded_backward reads the rows back as the same runs.
  *   frame.P = local Gaussian count; frame.row_* = this rank's CYCLIC band (row_begin == rank, row_step == world); S must be 0.
  *   peers->records[rank] is this rank's geom_state (sgr_state_sizes for P = world*chunk, `geom_bytes` bytes) whose first
- *   world*chunk records are the gather target; radii_local[chunk] / records_local[chunk] receive the rank's own results (kept
+ *   world*chunk records are the delivery target; radii_local[chunk] / records_local[chunk] receive the rank's own results (kept
  *   for sgr_sharded_backward).  Bounded mode only: `capacity` instances (binning_state of sgr_binning_bytes(capacity)) and
- *   `gaussian_capacity` depth-order slots (< 0: sort all world*chunk Gaussians; otherwise only the Gaussians with instances in
- *   this band are compacted and sorted — sgr_forward_status reports both counts and both overflow bits).
- *   barrier_epoch: epoch of the barrier after the scatter (0 = device-side count, see sgr_peer_barrier); with pre_barrier != 0 a
- *   barrier with epoch barrier_epoch - 1 (or the next device-side count) is issued first (needed when the previous call on this workspace was a forward without a backward: peers may still be reading the
- *   records this call overwrites).  The rows of peers->grad2d[rank] that a backward can touch are zeroed by this call. */
+ *   `gaussian_capacity` depth-order slots (< 0: world*chunk; the Gaussians delivered to this rank are compacted into them and
+ *   sorted — sgr_forward_status reports both counts and both overflow bits).
+ *   barrier_epoch: epoch of the barrier after the delivery (0 = device-side count, see sgr_peer_barrier); with pre_barrier != 0 a
+ *   barrier with epoch barrier_epoch - 1 (or the next device-side count) is issued first (needed when the previous call on this
+ *   workspace was a forward without a backward: peers may still be reading the records this call overwrites).  The rows of
+ *   peers->grad2d[rank] that a backward can touch are zeroed by this call.  No array needs a particular content on entry. */
 int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const float *means3D, const float *shs, const float *colors_precomp,
                         const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp, float *out_color,
                         float *out_depth, float *out_alpha, int32_t *radii_local, void *records_local, size_t geom_bytes, void *img_state,
@@ -239,7 +245,9 @@ int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const floa
                         uint32_t barrier_epoch, int32_t pre_barrier, void *stream);
 /* The matching backward as ONE call (steps 4-5): blend_bwd of the band into peers->grad2d[rank], device barrier (barrier_epoch), then
  * the per-Gaussian chain rule of the rank's frame.P Gaussians, which sums each Gaussian's 12 screen-space values from the
- * ranks that rendered it while it runs (no separate gather pass, no reduce-scatter).  Outputs as in sgr_backward_geom. */
+ * ranks that rendered it while it runs: every thread block fetches its runs of rows from those ranks' partial grad2d (contiguous,
+ * see sgr_sharded_forward) — no separate gather pass, no reduce-scatter.  Must follow the sgr_sharded_forward of the same frame on
+ * the same workspace (it re-derives the run positions from the destination masks that call kept).  Outputs as in sgr_backward_geom. */
 int sgr_sharded_backward(const SgrFrame *frame, const SgrPeers *peers, int64_t capacity, const float *means3D, const float *shs,
                          const float *colors_precomp, const float *scales, const float *rotations, const float *cov3D_precomp,
                          const int32_t *radii_local, const void *records_local, const void *img_state, const void *binning_state,

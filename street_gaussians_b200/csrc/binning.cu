@@ -187,6 +187,118 @@ cudaError_t launch_count_and_order(const FrameDev &f, GeomView g, const int32_t 
 	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, n, st);
 }
 
+// ---- fused Gaussian-sharded forward: the delivered runs (sgr_common.cuh "block-run exchange") -> compact depth-sort input ----
+// cnt[s * nblk + b] = number of records block b of owner s delivered to this rank (written by the owners' projection kernels before the
+// barrier).  One block turns the table into an exclusive prefix (entry e = first compact position of run e) and the total (status[4]).
+__global__ void __launch_bounds__(1024) run_prefix_kernel(const uint32_t *__restrict__ cnt, uint32_t *__restrict__ pre, const uint32_t entries,
+                                                          uint32_t *__restrict__ status) {
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0u;
+	__syncthreads();
+	for (uint32_t base = 0; base < entries; base += 1024u) {
+		const uint32_t e = base + threadIdx.x;
+		const uint32_t v = e < entries ? cnt[e] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t w = s_warp[lane];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+				if (lane >= o) w += t;
+			}
+			s_warp[lane] = w;  // inclusive prefix of the warp totals
+		}
+		__syncthreads();
+		const uint32_t carry = s_carry;
+		const uint32_t excl = carry + (warp ? s_warp[warp - 1] : 0u) + incl - v;
+		if (e < entries) pre[e] = excl;
+		__syncthreads();
+		if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) status[4] = s_carry;
+}
+
+// thread j = j-th delivered Gaussian in ascending slot order (= ascending global id): locate its run by binary search in the prefix table,
+// take the radius out of the record, count its tiles against this rank's band, write the depth-sort input and clear its grad2d row.
+__global__ void __launch_bounds__(256) count_runs_kernel(const FrameDev f, const GaussRec *__restrict__ rec, int32_t *__restrict__ radii,
+                                                        const uint32_t *__restrict__ pre, const uint32_t entries, const uint32_t nblk,
+                                                        const long long chunk, uint32_t *__restrict__ status, const uint32_t cap_v,
+                                                        uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ ckey,
+                                                        uint32_t *__restrict__ cval, float4 *__restrict__ zero_rows) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n_act = status[4];
+	if (j == 0 && n_act > cap_v) atomicOr(&status[2], 2u);
+	const bool live = j < n_act && j < cap_v;
+	bool ok = false;
+	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+	CullParams cp = {};
+	float depth = 0.f;
+	uint32_t gidx = 0u;
+	if (live) {
+		uint32_t lo = 0u, hi = entries;  // largest e with pre[e] <= j  (pre[0] = 0 <= j)
+		while (hi - lo > 1u) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (pre[mid] <= j) lo = mid; else hi = mid;
+		}
+		const uint32_t s = lo / nblk, b = lo - s * nblk;
+		gidx = (uint32_t)((long long)s * chunk + (long long)b * kRunBlock) + (j - pre[lo]);
+		const float4 q0 = rec[gidx].q0, q1 = rec[gidx].q1;
+		const int r = packed_radius(rec[gidx].q2.w);
+		radii[gidx] = r;  // emit_pairs / emit_big read the radius from here
+		tile_rect(q0.x, q0.y, r, f.gx, f.gy, x0, y0, x1, y1);
+		cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+		depth = q1.w;
+		ok = true;
+		if (zero_rows) {
+			const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+			zero_rows[3 * (size_t)gidx] = z; zero_rows[3 * (size_t)gidx + 1] = z; zero_rows[3 * (size_t)gidx + 2] = z;
+		}
+	}
+	uint32_t count = 0;
+	visit_tiles<false, uint32_t>(ok, x0, y0, x1, y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
+	if (j < cap_v) {
+		ckey[j] = (live && count > 0u) ? __float_as_uint(depth) : 0xffffffffu;
+		cval[j] = gidx;
+		if (live) tiles_touched[gidx] = count;
+	}
+}
+
+// g.iota = count table (filled by the owners), g.perm = its prefix (dead before the sort writes g.perm), cap_v < 0 -> all f.P slots
+cudaError_t launch_count_and_order_runs(const FrameDev &f, GeomView g, int32_t *radii, int world, long long chunk, cudaStream_t st, int64_t cap_v,
+                                        float *zero_rows, int *n_order) {
+	if (n_order) *n_order = f.P;
+	if (f.P == 0) return cudaSuccess;
+	const int n = (int)(cap_v < 0 ? (int64_t)f.P : (cap_v < 1 ? 1 : (cap_v > f.P ? f.P : cap_v)));
+	const uint32_t nblk = (uint32_t)((chunk + kRunBlock - 1) / kRunBlock);
+	const uint32_t entries = (uint32_t)world * nblk;
+	// the prefix table lives in g.offsets until the count kernel has consumed it (the scan below then overwrites it)
+	uint32_t *pre = g.offsets;
+	count_launch();
+	run_prefix_kernel<<<1, 1024, 0, st>>>(g.iota, pre, entries, g.big_count);
+	count_launch();
+	count_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, g.rec, radii, pre, entries, nblk, chunk, g.big_count, (uint32_t)n, g.tiles_touched,
+	                                                               g.ckey, g.cval, reinterpret_cast<float4 *>(zero_rows));
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	size_t bytes = g.temp_bytes;
+	e = cub::DeviceRadixSort::SortPairs(g.temp, bytes, g.ckey, g.depth_sorted, g.cval, g.perm, n, 0, 32, st);
+	if (e != cudaSuccess) return e;
+	if (n_order) *n_order = n;
+	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{g.tiles_touched, g.perm, g.depth_sorted});
+	bytes = g.temp_bytes;
+	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, n, st);
+}
+
 constexpr uint32_t kEmitStage = 512;  // instances staged per warp (2 x 2 KB of shared memory per warp)
 
 // thread t handles the t-th Gaussian in depth order.  KeyT = uint16_t whenever the image has at most 65,536 tiles (up to

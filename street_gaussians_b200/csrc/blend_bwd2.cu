@@ -19,25 +19,29 @@
 // matrix and triple-buffered records, so that phase 2 of batch b overlaps phase 1 of batch b+1.  The shared-memory budget forces
 // 16-splat batches (2 x 32 KB), i.e. 16 phase-2 threads per splat, a 4-step butterfly and twice the per-splat fixed cost:
 // 677 us vs 618 us for this kernel; 8-splat batches (4 CTAs/SM) 775 us; 32-splat double-buffered (1 CTA/SM) 1138 us.
-// Also measured (same kernel, SGR_BWD2_BATCH): 16-splat batches at 4 CTAs/SM 640 us, at 5 CTAs/SM (48 registers, 16 B spilled) 718 us,
+// Also measured (two-barrier kernel, templated on the batch size for the A/B): 16-splat batches at 4 CTAs/SM 640 us, at 5 CTAs/SM (48 registers, 16 B spilled) 718 us,
 // 32-splat batches with 79 registers 615 us, vs 613 us for the default (32 splats, 63 registers, 3 CTAs/SM).  More resident warps buy
 // nothing: the kernel is bound by the NUMBER of instructions it issues (76 % issue-active), not by latency.
 #include "sgr_common.cuh"
 
 namespace sgr {
 
+constexpr int kB2 = 32;  // splats per batch
 constexpr uint32_t kRec2 = 48;
-// shared-memory map of one CTA for a batch of B splats (B = 32: 75 KB, 3 CTAs/SM; B = 16: 40 KB, 4 CTAs/SM at 64 registers)
-template <int B>
-struct Smem2 {
-	static constexpr uint32_t kOffWQ = 0;                          // float2 [B][256]
-	static constexpr uint32_t kOffPix = B * 256 * 8;               // float4 [256]   dL/dpixel rgb, dL/dpixel depth
-	static constexpr uint32_t kOffPxy = kOffPix + 256 * 16;        // float2 [256]   pixel centre
-	static constexpr uint32_t kOffRec = kOffPxy + 256 * 8;         // [2][B * 48]    staged GaussRec
-	static constexpr uint32_t kOffId = kOffRec + 2 * B * kRec2;    // u32 [2][B]
-	static constexpr uint32_t kOffMask = kOffId + 2 * B * 4;       // u32 [8]        per-warp "slot has contributions" bits
-	static constexpr uint32_t kBytes = kOffMask + 8 * 4;
-};
+// Shared-memory map.  Phase 2 reads pixel i of chunk c (= the 8x4 block of warp c) at a COMPILE-TIME offset, so the 8 chunk-threads
+// of a splat (consecutive lanes) must land in different banks by layout, not by rotating the index: each 32-pixel chunk is padded by one
+// element (float2 rows: 66 words -> lanes 2 banks apart; float4 pixel gradients: 132 words -> lanes 4 banks apart) and the rows of
+// consecutive splats are 528 words = 16 banks apart, so a half-warp (2 splats x 8 chunks) of 8-byte loads and a quarter-warp of 16-byte
+// loads are conflict free.
+constexpr uint32_t kWQChunk = 33 * 8;                     // bytes per (splat, chunk): 32 x float2 + pad
+constexpr uint32_t kWQRow = 8 * kWQChunk;                 // bytes per splat
+constexpr uint32_t kPixChunk = 33 * 16;                   // bytes per chunk of float4 pixel gradients + pad
+constexpr uint32_t kOffWQ = 0;                            // float2 [kB2][8][33]   (w, q)
+constexpr uint32_t kOffPix = kB2 * kWQRow;                // float4 [8][33]        dL/dpixel rgb, dL/dpixel depth
+constexpr uint32_t kOffRec = kOffPix + 8 * kPixChunk;     // [2][kB2 * 48]         staged GaussRec
+constexpr uint32_t kOffId = kOffRec + 2 * kB2 * kRec2;    // u32 [2][kB2]
+constexpr uint32_t kOffMask = kOffId + 2 * kB2 * 4;       // u32 [8]               per-warp "slot has contributions" bits
+constexpr uint32_t kSmem2 = kOffMask + 8 * 4;             // 75168 B: 3 CTAs/SM
 
 __device__ __forceinline__ float4 ld4(uint32_t a) {
 	float4 v;
@@ -60,18 +64,14 @@ __device__ __forceinline__ void st4(uint32_t a, float4 v) {
 __device__ __forceinline__ void st2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
 __device__ __forceinline__ void stu(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-template <int kB2, int kMinCtas>
-__global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
+template <bool kFastExp>
+__global__ void __launch_bounds__(256, 3) blend_bwd2_kernel(const FrameDev f, const uint2 *__restrict__ ranges,
                                                          const uint32_t *__restrict__ point_list, const GaussRec *__restrict__ rec,
                                                          const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tile_max_contrib,
                                                          const float *__restrict__ alphas, const float *__restrict__ dL_dpixels,
                                                          const float *__restrict__ dL_dpixel_depths, const float *__restrict__ dL_dalphas,
                                                          float *__restrict__ grad2d) {
 	extern __shared__ __align__(16) unsigned char smem2[];
-	using L = Smem2<kB2>;
-	constexpr uint32_t kOffWQ = L::kOffWQ, kOffPix = L::kOffPix, kOffPxy = L::kOffPxy, kOffRec = L::kOffRec, kOffId = L::kOffId, kOffMask = L::kOffMask;
-	constexpr int kTPS = 256 / kB2;  // phase-2 threads per splat (8 or 16: consecutive lanes)
-	constexpr int kPPC = 256 / kTPS; // pixels per phase-2 thread (32 or 16)
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int tile_x = blockIdx.x, tile_y = f.band.begin + blockIdx.y * f.band.step;
 	const int tile = tile_y * f.gx + tile_x;
@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDe
 #pragma unroll
 	for (int c = 0; c < 3; c++) bg_dot_dpixel += f.bg[c] * dL_dpixel[c];
 	const float kW = 0.5f * f.W, kH = 0.5f * f.H;  // d(pixel)/d(NDC), reference backward.cu:501-502
-	st4(sb + kOffPix + (uint32_t)tid * 16u, make_float4(dL_dpixel[0], dL_dpixel[1], dL_dpixel[2], dL_dpixel_depth));
-	st2(sb + kOffPxy + (uint32_t)tid * 8u, pixf.x, pixf.y);
+	st4(sb + kOffPix + (uint32_t)warp * kPixChunk + (uint32_t)lane * 16u, make_float4(dL_dpixel[0], dL_dpixel[1], dL_dpixel[2], dL_dpixel_depth));
 
 	// staging: 4 threads per record (q0, q1, q2, id), threads 0..127; slot j of batch b <-> list index (n_eff - b*B) - 1 - j
 	const int ld_slot = tid >> 2, ld_part = tid & 3;
@@ -127,7 +126,9 @@ __global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDe
 	stash(0);
 
 	// phase-2 role of this thread
-	const int p2_slot = tid / kTPS, p2_chunk = tid % kTPS;
+	const int p2_slot = tid >> 3, p2_chunk = tid & 7;
+	// pixel (u, v) of chunk c sits at (cx0 + u, cy0 + v), u < 8, v < 4 — the lane order of phase 1
+	const float cx0 = (float)(tile_x * SGR_TILE + (p2_chunk & 1) * 8), cy0 = (float)(tile_y * SGR_TILE + (p2_chunk >> 1) * 4);
 
 	for (int b = 0; b < nb; b++) {
 		__syncthreads();  // record buffer b&1 published; phase 2 of the previous batch is done with s_wq / s_mask
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDe
 		// ---------------- phase 1: per-pixel recurrences -> (w, q) ----------------
 		uint32_t wmask = 0u;
 		uint32_t a = rbase;
-		uint32_t wq_addr = sb + kOffWQ + (uint32_t)tid * 8u;
-		for (int j = 0; j < cnt; j++, a += kRec2, wq_addr += 256u * 8u) {
+		uint32_t wq_addr = sb + kOffWQ + (uint32_t)warp * kWQChunk + (uint32_t)lane * 8u;
+		for (int j = 0; j < cnt; j++, a += kRec2, wq_addr += kWQRow) {
 			const int contributor = hi - 1 - j;
 			bool valid = contributor < last_contributor;
 			float q = 0.f, w = 0.f;
@@ -152,7 +153,12 @@ __global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDe
 				const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
 				valid = !(power > 0.0f) && !(power < q1.z);
 				if (valid) {
-					const float G = expf(power);
+					float G;
+					if (kFastExp) {  // A/B only (SGR_BWD2_FASTEXP=1): ex2.approx of power*log2(e), ~4e-7 relative instead of expf's 1 ulp
+						asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(power * 1.4426950408889634f));
+					} else {
+						G = expf(power);
+					}
 					const float alpha = fminf(0.99f, q1.y * G);
 					valid = !(alpha < 1.0f / 255.0f);
 					if (valid) {
@@ -191,40 +197,58 @@ __global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDe
 		// ---------------- phase 2: per-splat sums over the tile's pixels ----------------
 		{
 			float Sq = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sabs = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
-			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (uint32_t)(p2_chunk * kPPC / 32) * 4u) >> p2_slot) & 1u);
+			const bool live = p2_slot < cnt && ((ldu(sb + kOffMask + (uint32_t)p2_chunk * 4u) >> p2_slot) & 1u);
 			float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
 			if (live) {
 				r0 = ld4(rbase + (uint32_t)p2_slot * kRec2);
 				r1 = ld4(rbase + (uint32_t)p2_slot * kRec2 + 16);
-				const uint32_t row = sb + kOffWQ + (uint32_t)(p2_slot * 256 + p2_chunk * kPPC) * 8u;
-				const uint32_t pixb = sb + kOffPix + (uint32_t)(p2_chunk * kPPC) * 16u;
-				const uint32_t pxyb = sb + kOffPxy + (uint32_t)(p2_chunk * kPPC) * 8u;
-#pragma unroll 4
-				for (int i = 0; i < kPPC; i++) {
-					const uint32_t l = (uint32_t)(i + lane) & (uint32_t)(kPPC - 1);  // bank rotation: the lanes of a (half-)warp hit distinct pixels
-					const float2 wq = ld2(row + l * 8u);
-					const float4 pg = ld4(pixb + l * 16u);
-					const float2 pc = ld2(pxyb + l * 8u);
-					const float dx = r0.x - pc.x, dy = r0.y - pc.y;
-					const float qx = wq.y * dx, qy = wq.y * dy;
-					Sq += wq.y;
-					Sx += qx;
-					Sy += qy;
-					Sxx += qx * dx;
-					Sxy += qx * dy;
-					Syy += qy * dy;
-					Sabs += fabsf(wq.y) * (fabsf(r0.z * dx + r0.w * dy) * kW + fabsf(r1.x * dy + r0.w * dx) * kH);
-					Cr += wq.x * pg.x;
-					Cg += wq.x * pg.y;
-					Cb += wq.x * pg.z;
-					Cd += wq.x * pg.w;
+				const uint32_t row = sb + kOffWQ + (uint32_t)p2_slot * kWQRow + (uint32_t)p2_chunk * kWQChunk;
+				const uint32_t pixb = sb + kOffPix + (uint32_t)p2_chunk * kPixChunk;
+				// Moments are accumulated in the chunk's own integer pixel coordinates (u, v) — compile-time constants of the unrolled
+				// loops, so a pixel costs 3 FMAs instead of 8 and no coordinate load — and re-centred on the splat once at the end:
+				// d = (D - u, E - v) with (D, E) = centre - chunk origin.  |D - dx| <= 7, so the re-centring never cancels catastrophically.
+				const float D = r0.x - cx0, E = r0.y - cy0;
+				const float ca_ = r0.z, cb_ = r0.w, cc_ = r1.x;
+				const float A0 = fmaf(ca_, D, cb_ * E), B0 = fmaf(cc_, E, cb_ * D);  // a dx + b dy and c dy + b dx at (u, v) = (0, 0)
+				float M0 = 0.f, Mu = 0.f, Mv = 0.f, Muu = 0.f, Muv = 0.f, Mvv = 0.f;
+#pragma unroll
+				for (int v = 0; v < 4; v++) {
+					float R0 = 0.f, R1 = 0.f, R2 = 0.f;
+					const float Av = fmaf(-cb_, (float)v, A0), Bv = fmaf(-cc_, (float)v, B0);
+#pragma unroll
+					for (int u = 0; u < 8; u++) {
+						const uint32_t i = (uint32_t)(v * 8 + u);
+						const float2 wq = ld2(row + i * 8u);
+						const float4 pg = ld4(pixb + i * 16u);
+						R0 += wq.y;
+						R1 = fmaf(wq.y, (float)u, R1);
+						R2 = fmaf(wq.y, (float)(u * u), R2);
+						const float t1 = fmaf(-ca_, (float)u, Av), t2 = fmaf(-cb_, (float)u, Bv);
+						Sabs = fmaf(fabsf(wq.y), fmaf(fabsf(t1), kW, fabsf(t2) * kH), Sabs);
+						Cr = fmaf(wq.x, pg.x, Cr);
+						Cg = fmaf(wq.x, pg.y, Cg);
+						Cb = fmaf(wq.x, pg.z, Cb);
+						Cd = fmaf(wq.x, pg.w, Cd);
+					}
+					M0 += R0;
+					Mv = fmaf(R0, (float)v, Mv);
+					Mvv = fmaf(R0, (float)(v * v), Mvv);
+					Mu += R1;
+					Muv = fmaf(R1, (float)v, Muv);
+					Muu += R2;
 				}
+				Sq = M0;
+				Sx = fmaf(D, M0, -Mu);
+				Sy = fmaf(E, M0, -Mv);
+				Sxx = fmaf(D, fmaf(D, M0, -2.f * Mu), Muu);
+				Syy = fmaf(E, fmaf(E, M0, -2.f * Mv), Mvv);
+				Sxy = fmaf(D, fmaf(E, M0, -Mv), fmaf(-E, Mu, Muv));
 			}
 			// combine the 8 chunk-threads of each splat (consecutive lanes) — all lanes take part
 			const unsigned any_live = __ballot_sync(0xffffffffu, live);
 			if (any_live) {
 #pragma unroll
-				for (int o = 1; o < kTPS; o <<= 1) {
+				for (int o = 1; o < 8; o <<= 1) {
 					Sq += __shfl_xor_sync(0xffffffffu, Sq, o); Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
 					Sy += __shfl_xor_sync(0xffffffffu, Sy, o); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
 					Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o); Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
@@ -232,37 +256,28 @@ __global__ void __launch_bounds__(256, kMinCtas) blend_bwd2_kernel(const FrameDe
 					Cg += __shfl_xor_sync(0xffffffffu, Cg, o); Cb += __shfl_xor_sync(0xffffffffu, Cb, o);
 					Cd += __shfl_xor_sync(0xffffffffu, Cd, o);
 				}
-				// is any chunk of this splat live?  (bits of the kTPS lanes of this slot in the ballot)
-				const int g0 = lane & ~(kTPS - 1);
-				const unsigned grp = (any_live >> g0) & ((1u << kTPS) - 1u);
+				// is any chunk of this splat live?  (bits of the 8 lanes of this slot in the ballot)
+				const unsigned grp = (any_live >> (lane & 24)) & 0xffu;
 				// the conic / opacity of the splat: lanes that were not live did not load the record (all lanes shuffle)
-				const int srcl = grp != 0u ? g0 + (__ffs(grp) - 1) : lane;
+				const int srcl = grp != 0u ? (lane & 24) + (__ffs(grp) - 1) : lane;
 				const float ca = __shfl_sync(0xffffffffu, r0.z, srcl), cb = __shfl_sync(0xffffffffu, r0.w, srcl);
 				const float cc = __shfl_sync(0xffffffffu, r1.x, srcl), op = __shfl_sync(0xffffffffu, r1.y, srcl);
 				if (grp != 0u && p2_slot < cnt) {
 					const uint32_t gid = ldu(sb + kOffId + (uint32_t)(buf * kB2 + p2_slot) * 4u);
 					float *dst = grad2d + (size_t)gid * 12;
-					auto comp = [&](int k) -> float {  // component k of the grad2d row
-						switch (k) {
-							case 0: return -kW * (ca * Sx + cb * Sy);
-							case 1: return -kH * (cc * Sy + cb * Sx);
-							case 2: return Sabs;
-							case 3: return -0.5f * Sxx;
-							case 4: return -0.5f * Sxy;
-							case 5: return -0.5f * Syy;
-							case 6: return (op != 0.f) ? Sq / op : 0.f;
-							case 7: return Cr;
-							case 8: return Cg;
-							case 9: return Cb;
-							default: return Cd;
-						}
-					};
-					if (kTPS == 8) {  // lane c of the group writes components c and (c < 3) c + 8
-						atomicAdd(dst + p2_chunk, comp(p2_chunk));
-						if (p2_chunk < 3) atomicAdd(dst + 8 + p2_chunk, comp(8 + p2_chunk));
-					} else if (p2_chunk < 11) {
-						atomicAdd(dst + p2_chunk, comp(p2_chunk));
+					float o0, o1 = 0.f;
+					switch (p2_chunk) {  // lane c of the group writes components c and c + 8
+						case 0: o0 = -kW * (ca * Sx + cb * Sy); o1 = Cg; break;
+						case 1: o0 = -kH * (cc * Sy + cb * Sx); o1 = Cb; break;
+						case 2: o0 = Sabs; o1 = Cd; break;
+						case 3: o0 = -0.5f * Sxx; break;
+						case 4: o0 = -0.5f * Sxy; break;
+						case 5: o0 = -0.5f * Syy; break;
+						case 6: o0 = (op != 0.f) ? Sq / op : 0.f; break;
+						default: o0 = Cr; break;
 					}
+					atomicAdd(dst + p2_chunk, o0);
+					if (p2_chunk < 3) atomicAdd(dst + 8 + p2_chunk, o1);
 				}
 			}
 		}
@@ -278,23 +293,18 @@ cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView 
 	if (e != cudaSuccess) return e;
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
-	// batch size: 32 splats (75 KB of shared memory, 3 CTAs/SM) unless SGR_BWD2_BATCH=16 (40 KB, 4 CTAs/SM) — A/B'd in round 2
-	//             SGR_BWD2_BATCH=165: 16 splats with the register budget of 5 CTAs/SM
-	static const int batch = [] { const char *e = getenv("SGR_BWD2_BATCH"); const int v = e ? atoi(e) : 32; return (v == 16 || v == 165 || v == 323) ? v : 32; }();
-	static std::atomic<uint64_t> configured32{0}, configured16{0}, configured165{0}, configured323{0};
+	static const bool fast_exp = [] { const char *v = getenv("SGR_BWD2_FASTEXP"); return v && atoi(v) == 1; }();
+	static std::atomic<uint64_t> configured{0}, configured_fast{0};
 	count_launch();
-#define SGR_LAUNCH_BWD2(B, C, FLAG)                                                                                                         \
-	do {                                                                                                                                    \
-		if ((e = ensure_dynamic_smem(blend_bwd2_kernel<B, C>, (int)Smem2<B>::kBytes, FLAG)) != cudaSuccess) return e;                       \
-		blend_bwd2_kernel<B, C><<<dim3(f.gx, rows), 256, Smem2<B>::kBytes, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib,            \
-		                                                                        img.tile_max_contrib, out_alpha, dL_dcolor, dL_ddepth,       \
-		                                                                        dL_dalpha, grad2d);                                          \
-	} while (0)
-	if (batch == 16) SGR_LAUNCH_BWD2(16, 4, configured16);
-	else if (batch == 165) SGR_LAUNCH_BWD2(16, 5, configured165);
-	else if (batch == 323) SGR_LAUNCH_BWD2(32, 3, configured323);  // 32 splats, up to 85 registers
-	else SGR_LAUNCH_BWD2(32, 4, configured32);                     // 32 splats, 64 registers (3 CTAs/SM by shared memory)
-#undef SGR_LAUNCH_BWD2
+	if (fast_exp) {
+		if ((e = ensure_dynamic_smem(blend_bwd2_kernel<true>, (int)kSmem2, configured_fast)) != cudaSuccess) return e;
+		blend_bwd2_kernel<true><<<dim3(f.gx, rows), 256, kSmem2, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, img.tile_max_contrib,
+		                                                              out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, grad2d);
+	} else {
+		if ((e = ensure_dynamic_smem(blend_bwd2_kernel<false>, (int)kSmem2, configured)) != cudaSuccess) return e;
+		blend_bwd2_kernel<false><<<dim3(f.gx, rows), 256, kSmem2, st>>>(f, img.ranges, b.vals_out, g.rec, img.n_contrib, img.tile_max_contrib,
+		                                                               out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, grad2d);
+	}
 	return cudaGetLastError();
 }
 

@@ -414,20 +414,20 @@ int sgr_sharded_forward(const SgrFrame *frame, const SgrPeers *peers, const floa
 		return fail(SGR_ENOMEM, "binning_state too small for capacity %lld: %zu < %zu", (long long)capacity, binning_bytes, need);
 	// a forward that follows a forward (no backward in between) must not overwrite records a peer may still be blending
 	if (pre_barrier) SGR_TRY(launch_peer_barrier(pt, barrier_epoch ? barrier_epoch - 1u : 0u, nullptr, st), "pre-barrier");
+	// (g.depth_key of this rank = the destination masks of its own Gaussians, kept for the backward; g.iota of rank d = the run-length
+	// table the owners fill — same offset inside every rank's geom state)
 	SGR_TRY(launch_project_scatter(fl, pt, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii_local,
-	                               reinterpret_cast<GaussRec *>(records_local), st),
+	                               reinterpret_cast<GaussRec *>(records_local), g.depth_key,
+	                               (size_t)(reinterpret_cast<char *>(g.iota) - reinterpret_cast<char *>(geom_state)), st),
 	        "project+scatter");
 	if (ft.P == 0) return SGR_OK;
 	SGR_TRY(cudaMemsetAsync(g.big_count, 0, 64 * sizeof(uint32_t), st), "status reset");
 	SGR_TRY(launch_peer_barrier(pt, barrier_epoch, g.big_count, st), "barrier");
 	int n_order = ft.P;
-	SGR_TRY(launch_count_and_order(ft, g, pt.radii[pt.rank], st, gaussian_capacity, const_cast<float *>(pt.grad2d[pt.rank]), &n_order), "count + depth_order");
+	SGR_TRY(launch_count_and_order_runs(ft, g, pt.radii[pt.rank], pt.world, pt.chunk, st, gaussian_capacity, const_cast<float *>(pt.grad2d[pt.rank]), &n_order),
+	        "count + depth_order");
 	const BinView b = capacity > 0 ? carve_bin(binning_state, capacity) : carve_bin(nullptr, 0);
 	SGR_TRY(launch_binning(ft, g, pt.radii[pt.rank], b, img, capacity, st, capacity, n_order), "binning");
-	// the delivered radii have been consumed (count, emit): clear them for the next frame's owners, who only store to the ranks they
-	// deliver to.  No peer writes this array before it has passed a barrier this rank reaches after this memset (the backward's,
-	// or the leading barrier of a forward that follows a forward).
-	SGR_TRY(cudaMemsetAsync(pt.radii[pt.rank], 0, (size_t)ft.P * sizeof(int32_t), st), "radii reset");
 	SGR_TRY(launch_blend_fwd(ft, g, b, img, nullptr, out_color, out_depth, out_alpha, nullptr, st), "blend_fwd");
 	return SGR_OK;
 }
@@ -463,7 +463,7 @@ int sgr_sharded_backward(const SgrFrame *frame, const SgrPeers *peers, int64_t c
 	SGR_TRY(launch_preprocess_bwd_gather(fl, pt, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii_local,
 	                                     reinterpret_cast<const GaussRec *>(records_local), dL_dmeans3D, dL_dmeans2D, shs ? dL_dsh : nullptr,
 	                                     dL_dcolors_precomp, dL_dopacity, cov3D_precomp ? nullptr : dL_dscales,
-	                                     cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, st),
+	                                     cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, g.depth_key, st),
 	        "preprocess_bwd+gather");
 	return SGR_OK;
 }

@@ -38,6 +38,37 @@ __device__ __forceinline__ M3 rot_colmajor(const float4 q) {
 constexpr int kShRow = 49;  // padded smem row (floats) for up to 16 x 3 SH coefficients
 constexpr int kBwdStride = 52;  // row stride (floats) of the TMA variant's stage: 208 B
 
+// Block-run gather (sgr_common.cuh): the rows this block's Gaussians accumulated on rank d are the first c(d) rows of the block's 256
+// slots in rank d's partial grad2d — one contiguous run per rank, fetched with lane-contiguous 16-B loads (whole 128-B lines over
+// NVLink) into shared memory, 256 rows per round; every thread then adds its own rows in ascending rank order.  Collective over the
+// block; `mask` must be the destination mask the forward stored for this thread's Gaussian (0 for none).
+__device__ __forceinline__ void gather_runs(const PeerTable &pt, const uint32_t mask, RunScratch &rs, float4 *s_g, float4 &g0v, float4 &g1v,
+                                            float4 &g2v) {
+	block_run_ranks(rs, mask, pt.world);
+	const uint32_t total = rs.cpre[pt.world];
+	const size_t slot0 = (size_t)pt.rank * (size_t)pt.chunk + (size_t)blockIdx.x * kRunBlock;
+	for (uint32_t base = 0; base < total; base += kRunBlock) {
+		const uint32_t n = min((uint32_t)kRunBlock, total - base);
+		for (uint32_t e = threadIdx.x; e < 3u * n; e += kRunBlock) {
+			const uint32_t pos = base + e / 3u, part = e % 3u;
+			const int d = run_dest(rs, pos, pt.world);
+			s_g[e] = reinterpret_cast<const float4 *>(pt.grad2d[d] + (slot0 + (pos - rs.cpre[d])) * 12)[part];
+		}
+		__syncthreads();
+		for (int d = 0; d < pt.world; d++) {
+			const uint32_t r = run_rank(rs, mask, d);
+			const uint32_t pos = rs.cpre[d] + r;
+			if (((mask >> d) & 1u) && pos >= base && pos < base + kRunBlock) {
+				const float4 a = s_g[(pos - base) * 3u], b = s_g[(pos - base) * 3u + 1u], c = s_g[(pos - base) * 3u + 2u];
+				g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
+				g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
+				g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
+			}
+		}
+		__syncthreads();
+	}
+}
+
 // GATHER = true (sgr_sharded_backward): grad2d is not a local array — the 12 sums of local Gaussian idx (global id
 // rank*chunk + idx) are read from the partial grad2d of every rank whose cyclic band its rectangle meets (NVLink peer loads)
 // and added in ascending rank order, exactly what sgr_gather_grad2d produced as a separate pass.
@@ -85,24 +116,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 	}
 
 	float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, g2v = g0v;
+	if (GATHER) {  // (`grad2d` carries the destination masks the forward stored)
+		__shared__ RunScratch rs;
+		__shared__ float4 s_g[3 * kRunBlock];
+		const uint32_t mask = visible ? reinterpret_cast<const uint32_t *>(grad2d)[idx] : 0u;
+		gather_runs(pt, mask, rs, s_g, g0v, g1v, g2v);
+	}
 	if (in_range) {
-		if (GATHER) {
-			if (visible) {
-				int x0, y0, x1, y1;
-				const float4 q0 = rec[idx].q0;
-				tile_rect(q0.x, q0.y, radii[idx], f.gx, f.gy, x0, y0, x1, y1);
-				const uint32_t mask = x1 > x0 ? touched_ranks(y0, y1, pt.world) : 0u;
-				const size_t g = (size_t)pt.rank * (size_t)pt.chunk + i;
-				for (int p = 0; p < pt.world; p++) {
-					if (!((mask >> p) & 1u)) continue;
-					const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + g * 12);
-					const float4 a = src[0], b = src[1], c = src[2];
-					g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
-					g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
-					g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
-				}
-			}
-		} else {
+		if (!GATHER) {
 			g0v = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
 			g1v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
 			g2v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
@@ -241,7 +262,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 	if (shs != nullptr) {
 		const float *sh = STAGED ? srow : shs + i * nsh;
 		float *dsh = STAGED ? srow : dL_dsh + i * nsh;
-		const uint32_t clamp_bits = __float_as_uint(rec[idx].q2.w);
+		const uint32_t clamp_bits = __float_as_uint(rec[idx].q2.w) & 7u;  // (the fused forward keeps the radius in the upper bits)
 		const float3 campos = make_float3(f.campos[0], f.campos[1], f.campos[2]);
 		const float3 dir_orig = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
 		const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -410,7 +431,6 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_tma_kernel(
 	float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
 	float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 	uint32_t clamp_bits = 0u;
-	float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (in_range) {
 		radius = radii[idx];
 		mean = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
@@ -421,9 +441,8 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_tma_kernel(
 			q = *reinterpret_cast<const float4 *>(rotations + 4 * i);
 			sc = make_float3(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]);
 		}
-		clamp_bits = __float_as_uint(rec[idx].q2.w);
-		if (GATHER) q0 = rec[idx].q0;
-		else {
+		clamp_bits = __float_as_uint(rec[idx].q2.w) & 7u;  // (the fused forward keeps the radius in the upper bits)
+		if (!GATHER) {
 			g0v = reinterpret_cast<const float4 *>(grad2d)[3 * i];      // mean2D.x, .y, .z(abs), conic.xx
 			g1v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 1];  // conic.xy, conic.yy, opacity, color.r
 			g2v = reinterpret_cast<const float4 *>(grad2d)[3 * i + 2];  // color.g, color.b, depth, pad
@@ -435,62 +454,11 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_tma_kernel(
 	__syncthreads();
 	const float *view = s_cam, *proj = s_cam + 16;
 	const bool visible = in_range && radius > 0;
-	if (GATHER) {
-		// The 12-float rows of a warp's 32 Gaussians are 1536 contiguous bytes in every rank's partial grad2d.  Read per lane they are
-		// three 16-B loads at a 48-B stride (half-used sectors, and over NVLink each a separate request); when at least half of the
-		// lanes need rank p the warp fetches the whole block with lane-contiguous 16-B loads into shared memory and each lane picks its
-		// row (rows of lanes that do not need rank p are stale there and are simply not read).
-		__shared__ float4 s_g[8][96];
-		uint32_t mask = 0u;
-		if (visible) {
-			int x0, y0, x1, y1;
-			tile_rect(q0.x, q0.y, radius, f.gx, f.gy, x0, y0, x1, y1);
-			mask = x1 > x0 ? touched_ranks(y0, y1, pt.world) : 0u;
-		}
-		const size_t g = (size_t)pt.rank * (size_t)pt.chunk + i;
-		const bool full_warp = rows == 32;
-		// dense destinations first (block fetch through shared memory), remembering which peers are left for this lane
-		uint32_t left = mask;
-		for (int p = 0; p < pt.world; p++) {
-			const bool hit = (mask >> p) & 1u;
-			const unsigned hits = __ballot_sync(0xffffffffu, hit);
-			if (!(full_warp && __popc(hits) >= 16)) continue;
-			const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[p] + (g - (size_t)lane) * 12);
-#pragma unroll
-			for (int k = 0; k < 3; k++) s_g[warp][k * 32 + lane] = src[k * 32 + lane];
-			__syncwarp();
-			if (hit) {
-				const float4 a = s_g[warp][lane * 3], b = s_g[warp][lane * 3 + 1], c = s_g[warp][lane * 3 + 2];
-				g0v.x += a.x; g0v.y += a.y; g0v.z += a.z; g0v.w += a.w;
-				g1v.x += b.x; g1v.y += b.y; g1v.z += b.z; g1v.w += b.w;
-				g2v.x += c.x; g2v.y += c.y; g2v.z += c.z; g2v.w += c.w;
-				left &= ~(1u << p);
-			}
-			__syncwarp();
-		}
-		// sparse destinations (the N = 8 case: one or two ranks per Gaussian): the rows of up to three peers are requested TOGETHER and
-		// summed in ascending rank order afterwards — one NVLink round trip instead of one per peer (94 us -> see profiles/r02_summary.md)
-		while (left != 0u) {
-			int pp[3];
-			float4 v[3][3];
-#pragma unroll
-			for (int k = 0; k < 3; k++) {
-				pp[k] = left ? __ffs(left) - 1 : -1;
-				if (pp[k] >= 0) {
-					left &= left - 1u;
-					const float4 *src = reinterpret_cast<const float4 *>(pt.grad2d[pp[k]] + g * 12);
-					v[k][0] = src[0]; v[k][1] = src[1]; v[k][2] = src[2];
-				}
-			}
-#pragma unroll
-			for (int k = 0; k < 3; k++) {
-				if (pp[k] >= 0) {
-					g0v.x += v[k][0].x; g0v.y += v[k][0].y; g0v.z += v[k][0].z; g0v.w += v[k][0].w;
-					g1v.x += v[k][1].x; g1v.y += v[k][1].y; g1v.z += v[k][1].z; g1v.w += v[k][1].w;
-					g2v.x += v[k][2].x; g2v.y += v[k][2].y; g2v.z += v[k][2].z; g2v.w += v[k][2].w;
-				}
-			}
-		}
+	if (GATHER) {  // (`grad2d` carries the destination masks the forward stored)
+		__shared__ RunScratch rs;
+		__shared__ float4 s_g[3 * kRunBlock];
+		const uint32_t mask = visible ? reinterpret_cast<const uint32_t *>(grad2d)[idx] : 0u;
+		gather_runs(pt, mask, rs, s_g, g0v, g1v, g2v);
 	}
 	const float4 g0 = g0v, g1 = g1v, g2 = g2v;
 	if (in_range) {
@@ -749,15 +717,16 @@ cudaError_t launch_preprocess_bwd_gather(const FrameDev &f, const PeerTable &pt,
                                          const float *colors_precomp, const float *scales, const float *rotations,
                                          const float *cov3D_precomp, const int32_t *radii, const GaussRec *rec, float *dL_dmeans3D,
                                          float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
-                                         float *dL_drot, float *dL_dcov3D, cudaStream_t st) {
+                                         float *dL_drot, float *dL_dcov3D, const uint32_t *masks_local, cudaStream_t st) {
 	if (f.P == 0) return cudaSuccess;
+	const float *masks = reinterpret_cast<const float *>(masks_local);  // travels in the kernels' (otherwise unused) grad2d parameter
 	if (bwd_rows_fit_tma(f, shs, dL_dsh)) {
 		static std::atomic<uint64_t> configured{0};
 		cudaError_t e = ensure_dynamic_smem(preprocess_bwd_tma_kernel<true>, (int)kBwdStageBytes, configured);
 		if (e != cudaSuccess) return e;
 		count_launch();
 		preprocess_bwd_tma_kernel<true><<<(f.P + 255) / 256, 256, kBwdStageBytes, st>>>(f, pt, means3D, shs, scales, rotations, cov3D_precomp, radii, rec,
-		                                                                               nullptr, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dopacity,
+		                                                                               masks, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dopacity,
 		                                                                               dL_dscales, dL_drot, dL_dcov3D);
 		return cudaGetLastError();
 	}
@@ -769,12 +738,12 @@ cudaError_t launch_preprocess_bwd_gather(const FrameDev &f, const PeerTable &pt,
 		if (e != cudaSuccess) return e;
 		count_launch();
 		preprocess_bwd_kernel<true, true><<<(f.P + 255) / 256, 256, smem, st>>>(f, pt, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
-		                                                                        radii, rec, nullptr, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+		                                                                        radii, rec, masks, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 		                                                                        dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
 	} else {
 		count_launch();
 		preprocess_bwd_kernel<false, true><<<(f.P + 255) / 256, 256, 0, st>>>(f, pt, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp,
-		                                                                      radii, rec, nullptr, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+		                                                                      radii, rec, masks, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 		                                                                      dL_dopacity, dL_dscales, dL_drot, dL_dcov3D);
 	}
 	return cudaGetLastError();

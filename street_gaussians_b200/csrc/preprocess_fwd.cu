@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
                                                              const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                                                              int32_t *__restrict__ radii, GaussRec *__restrict__ rec,
                                                              uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ depth_key,
-                                                             uint32_t *__restrict__ iota) {
+                                                             uint32_t *__restrict__ iota, const size_t cnt_offset = 0) {
 	extern __shared__ __align__(16) unsigned char s_stage[];  // TMA: [8 warps][32 rows][kShStride floats] + 8 mbarriers
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = idx < f.P;
@@ -283,52 +283,49 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const FrameDev f, c
 		radii[idx] = pr.radius;
 	}
 	if (SCATTER) {
-		// The 48-B records of a warp are 1536 contiguous bytes in every destination array (global ids are consecutive).  Written as
-		// three float4 per LANE they are 32 half-filled sectors per store instruction — over NVLink that cost 152 us for 0.95 M
-		// Gaussians at N = 2 (300 GB/s, trace in profiles/r02_summary.md).  Staged through shared memory the warp writes whole 128-B
-		// lines (96 x 16 B, lane-contiguous) whenever at least half of its lanes go to that rank — the slots of the other lanes receive
-		// a record nobody reads (their radius on that rank is 0); sparse destinations (N = 8: one or two ranks per Gaussian) keep
-		// per-lane stores.
+		// Block-run delivery (sgr_common.cuh): the records of this block that rank d needs leave as ONE contiguous run into the block's
+		// 256 slots of rank d's gathered array, copied out of shared memory as lane-contiguous 16-B pieces (whole 128-B lines), and the
+		// run lengths go to rank d's count table.  Round-2 history (profiles/r02_summary.md): per-lane 48-B stores at the global index
+		// 152 us for 0.95 M Gaussians at N = 2; warp-staged lines / packed 48-B runs + per-Gaussian radius stores 75 us + 65 us of
+		// NVLink drain in the barrier for 237 k Gaussians at N = 8.
+		// Here `depth_key` = this rank's destination masks (kept for the backward), `iota`/cnt_offset = the count tables.
 		__shared__ float4 s_out[8][96];
+		__shared__ RunScratch rs;
+		__shared__ uint8_t s_src[kRunBlock * kMaxPeers];
 		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 		const bool slot = (long long)idx < pt.chunk;
 		const uint32_t mask = pr.ok ? touched_ranks(pr.y0, pr.y1, pt.world) : 0u;
-		const size_t g = (size_t)pt.rank * (size_t)pt.chunk + (size_t)idx;
+		rec_out.q2.w = pack_radius_clamp(pr.ok ? pr.radius : 0, __float_as_uint(rec_out.q2.w));
 		s_out[warp][lane * 3] = rec_out.q0; s_out[warp][lane * 3 + 1] = rec_out.q1; s_out[warp][lane * 3 + 2] = rec_out.q2;
-		__syncwarp();
-		const bool full_warp = __all_sync(0xffffffffu, in_range);
-		const size_t g0 = g - (size_t)lane;
-		if (full_warp) {  // own copy (kept for the backward): always all 32 records
-			float4 *dst = reinterpret_cast<float4 *>(rec + (idx - lane));
-#pragma unroll
-			for (int k = 0; k < 3; k++) dst[k * 32 + lane] = s_out[warp][k * 32 + lane];
-		} else if (in_range && pr.ok) {
-			rec[idx] = rec_out;
-		}
-		// Radii go ONLY to the ranks that receive the record: every rank clears its radii_all after it has binned a frame
-		// (sgr_sharded_forward), so "not delivered" is the zero that is already there.  The round-2 first cut stored a radius
-		// (mostly 0) to all N ranks: 8 remote 128-B lines per warp at N = 8, 103 us for 237 k Gaussians (profiles/r02_summary.md).
-		for (int p = 0; p < pt.world; p++) {
-			const bool hit = (mask >> p) & 1u;
-			const unsigned hits = __ballot_sync(0xffffffffu, hit);
-			if (hits == 0u) continue;
-			const int n_hit = __popc(hits);
-			if (full_warp && n_hit >= 16) {
-				float4 *dst = reinterpret_cast<float4 *>(pt.rec[p] + g0);
-#pragma unroll
-				for (int k = 0; k < 3; k++) dst[k * 32 + lane] = s_out[warp][k * 32 + lane];
-			} else {
-				// sparse destination: piece e = 3 * (rank of the record among the hit lanes) + (16-B third of it); consecutive lanes
-				// write consecutive thirds, so a record leaves as ONE 48-B run instead of three half-filled sectors in three stores
-				for (int e = lane; e < 3 * n_hit; e += 32) {
-					const int which = e / 3, piece = e - 3 * which;
-					const int src_lane = __fns(hits, 0, which + 1);
-					reinterpret_cast<float4 *>(pt.rec[p] + g0 + src_lane)[piece] = s_out[warp][src_lane * 3 + piece];
-				}
-			}
-			if (hit) pt.radii[p][g] = pr.radius;
-		}
+		if (slot) depth_key[idx] = mask;
 		if (slot && !in_range) radii[idx] = 0;  // padding slot of the local arrays
+		block_run_ranks(rs, mask, pt.world);    // (contains the barriers that publish s_out)
+		// own copy, kept for the backward (all 256 records, coalesced)
+		{
+			const long long first = (long long)blockIdx.x * kRunBlock;
+			const int nrec = (int)min((long long)kRunBlock, (long long)f.P - first);
+			float4 *dst = reinterpret_cast<float4 *>(rec + first);
+			const float4 *src = &s_out[0][0];
+			for (int e = threadIdx.x; e < 3 * nrec; e += kRunBlock) dst[e] = src[e];
+		}
+		for (int d = 0; d < pt.world; d++) {
+			const uint32_t r = run_rank(rs, mask, d);
+			if ((mask >> d) & 1u) s_src[rs.cpre[d] + r] = (uint8_t)threadIdx.x;
+		}
+		__syncthreads();
+		const uint32_t total = rs.cpre[pt.world];
+		const size_t slot0 = (size_t)pt.rank * (size_t)pt.chunk + (size_t)blockIdx.x * kRunBlock;
+		for (uint32_t e = threadIdx.x; e < 3u * total; e += kRunBlock) {
+			const uint32_t pos = e / 3u, part = e - 3u * pos;
+			const int d = run_dest(rs, pos, pt.world);
+			const uint32_t t = s_src[pos];
+			reinterpret_cast<float4 *>(pt.rec[d] + slot0 + (pos - rs.cpre[d]))[part] = s_out[t >> 5][(t & 31u) * 3u + part];
+		}
+		if ((int)threadIdx.x < pt.world) {
+			uint32_t *cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(pt.rec[threadIdx.x]) + cnt_offset);
+			const uint32_t nblk = (uint32_t)((pt.chunk + kRunBlock - 1) / kRunBlock);
+			cnt[(size_t)pt.rank * nblk + blockIdx.x] = rs.cpre[threadIdx.x + 1] - rs.cpre[threadIdx.x];
+		}
 	}
 	if (!COUNT) return;
 	uint32_t count = 0;
@@ -415,19 +412,21 @@ cudaError_t launch_project(const FrameDev &f, const float *means3D, const float 
 }
 cudaError_t launch_project_scatter(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
                                    const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
-                                   const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, cudaStream_t st) {
+                                   const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, uint32_t *masks_local,
+                                   size_t cnt_offset, cudaStream_t st) {
 	if (pt.chunk == 0) return cudaSuccess;
 	count_launch();
-	const unsigned nblk = (unsigned)((pt.chunk + 255) / 256);
+	const unsigned nblk = (unsigned)((pt.chunk + kRunBlock - 1) / kRunBlock);
 	if (sh_rows_fit_tma(f, shs)) {
 		static std::atomic<uint64_t> configured{0};
 		cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<false, true, true>, (int)kFwdStageBytes, configured);
 		if (e != cudaSuccess) return e;
 		preprocess_fwd_kernel<false, true, true><<<nblk, 256, kFwdStageBytes, st>>>(f, pt, means3D, shs, colors_precomp, opacities, scales, rotations,
-		                                                                          cov3D_precomp, radii_local, rec_local, nullptr, nullptr, nullptr);
+		                                                                          cov3D_precomp, radii_local, rec_local, nullptr, masks_local, nullptr,
+		                                                                          cnt_offset);
 	} else {
 		preprocess_fwd_kernel<false, true><<<nblk, 256, 0, st>>>(f, pt, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-		                                                         radii_local, rec_local, nullptr, nullptr, nullptr);
+		                                                         radii_local, rec_local, nullptr, masks_local, nullptr, cnt_offset);
 	}
 	return cudaGetLastError();
 }

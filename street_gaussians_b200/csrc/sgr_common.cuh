@@ -212,6 +212,9 @@ cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
 cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
 cudaError_t launch_count_and_order(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st, int64_t cap_v, float *zero_rows, int *n_order);
+// fused Gaussian-sharded forward: tile counts + depth order of the runs delivered to this rank (binning.cu)
+cudaError_t launch_count_and_order_runs(const FrameDev &f, GeomView g, int32_t *radii, int world, long long chunk, cudaStream_t st, int64_t cap_v,
+                                        float *zero_rows, int *n_order);
 // Gaussian-sharded exchange over peer memory (peer_exchange.cu); device copy of include/sgr.h's SgrPeers
 constexpr int kMaxPeers = 16;
 struct PeerTable {
@@ -230,18 +233,73 @@ __device__ __forceinline__ uint32_t touched_ranks(int y0, int y1, int world) {
 	for (int y = y0; y < y1; y++) m |= 1u << (y % world);
 	return m;
 }
+// ---- block-run exchange of the fused Gaussian-sharded step (sgr_sharded_forward / sgr_sharded_backward) -------------------------------
+// The 256 consecutive Gaussians of one thread block that go to rank d are delivered as ONE contiguous run: block b of owner s owns the
+// 256 slots [s*chunk + b*256, +256) of every rank's gathered arrays and fills the first c(s, b, d) of them on rank d, in ascending
+// Gaussian order.  Ascending slot order therefore equals ascending global-id order (the tie order of the depth sort on one GPU), the
+// records of a run leave the SM as whole 128-B lines (48-B records stored one by one cost ~0.5 of a NVLink packet each: 75 us of
+// stores + 65 us of drain for 237 k Gaussians at N = 8), and in the backward the owner reads its rows back as the same runs.
+// The radius travels in the record (q2.w = radius << 3 | colour-clamp bits); no per-Gaussian array is indexed by the global id.
+constexpr int kRunBlock = 256;
+__device__ __forceinline__ float pack_radius_clamp(int radius, uint32_t clamp_bits) { return __uint_as_float(((uint32_t)radius << 3) | (clamp_bits & 7u)); }
+__device__ __forceinline__ int packed_radius(float w) { return (int)(__float_as_uint(w) >> 3); }
+struct RunScratch {
+	uint32_t wcnt[8][kMaxPeers];   // per warp, per destination: hits of the lower warps (exclusive prefix after block_run_ranks)
+	uint32_t cpre[kMaxPeers + 1];  // per destination: first position of its run in the block's concatenated run list; [world] = total
+};
+// Collective over the 256 threads of a block (every thread calls it, `mask` = destinations of this thread's Gaussian, 0 if none).
+// Afterwards the position of this thread's record in destination d's run is  run_rank(rs, mask, d).
+__device__ __forceinline__ void block_run_ranks(RunScratch &rs, uint32_t mask, int world) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int d = 0; d < world; d++) {
+		const unsigned b = __ballot_sync(0xffffffffu, (mask >> d) & 1u);
+		if (lane == 0) rs.wcnt[warp][d] = (uint32_t)__popc(b);
+	}
+	__syncthreads();
+	if ((int)threadIdx.x < world) {
+		uint32_t run = 0u;
+		for (int w = 0; w < 8; w++) {
+			const uint32_t t = rs.wcnt[w][threadIdx.x];
+			rs.wcnt[w][threadIdx.x] = run;
+			run += t;
+		}
+		rs.cpre[threadIdx.x + 1] = run;  // count of destination d, turned into a prefix below
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0u;
+		rs.cpre[0] = 0u;
+		for (int d = 0; d < world; d++) {
+			const uint32_t c = rs.cpre[d + 1];
+			rs.cpre[d + 1] = acc + c;
+			acc += c;
+		}
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ uint32_t run_rank(const RunScratch &rs, uint32_t mask, int d) {
+	const unsigned b = __ballot_sync(0xffffffffu, (mask >> d) & 1u);  // (all lanes of the warp call this together)
+	return rs.wcnt[threadIdx.x >> 5][d] + (uint32_t)__popc(b & ((1u << (threadIdx.x & 31)) - 1u));
+}
+// destination of position `pos` of the block's concatenated run list
+__device__ __forceinline__ int run_dest(const RunScratch &rs, uint32_t pos, int world) {
+	int d = 0;
+	while (d + 1 < world && pos >= rs.cpre[d + 1]) d++;
+	return d;
+}
 cudaError_t launch_peer_barrier(const PeerTable &pt, uint32_t epoch, uint32_t *status, cudaStream_t st);
 // sgr_project fused with sgr_scatter_records: one pass over the rank's chunk (f.P local Gaussians, pt.chunk slots)
 cudaError_t launch_project_scatter(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
                                    const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
-                                   const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, cudaStream_t st);
+                                   const float *cov3D_precomp, int32_t *radii_local, GaussRec *rec_local, uint32_t *masks_local,
+                                   size_t cnt_offset, cudaStream_t st);
 // sgr_gather_grad2d fused into sgr_backward_geom: the 12 screen-space sums of each local Gaussian are summed from the ranks
 // that rendered it while the chain rule runs
 cudaError_t launch_preprocess_bwd_gather(const FrameDev &f, const PeerTable &pt, const float *means3D, const float *shs,
                                          const float *colors_precomp, const float *scales, const float *rotations,
                                          const float *cov3D_precomp, const int32_t *radii, const GaussRec *rec, float *dL_dmeans3D,
                                          float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
-                                         float *dL_drot, float *dL_dcov3D, cudaStream_t st);
+                                         float *dL_drot, float *dL_dcov3D, const uint32_t *masks_local, cudaStream_t st);
 cudaError_t launch_scatter_records(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, cudaStream_t st);
 cudaError_t launch_gather_grad2d(const FrameDev &f, const PeerTable &pt, const GaussRec *rec, const int32_t *radii, float *out,
                                  cudaStream_t st);

@@ -250,7 +250,7 @@ class PeerWorkspace:
             import torch.distributed._symmetric_memory as symm
             self.buf = symm.empty(self.total, dtype=torch.uint8, device=device)
             self.buf[self.off_flags:].zero_()  # barrier pads start at epoch 0
-            self.buf[self.off_radii: self.off_grad].zero_()  # sgr_sharded_forward's invariant: radii_all is all zero on entry
+            self.buf[self.off_radii: self.off_grad].zero_()
             self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
             ptrs = list(self.hdl.buffer_ptrs)
             self.hdl.barrier(channel=0)  # every pad is zero before any rank can send its first epoch
@@ -529,12 +529,7 @@ def _fused_forward(ctx, tensors, settings, owner, ws: "PeerWorkspace", P: int, c
     cap = owner.capacity
     if not cap.frozen:
         cap.check()
-    if ws.radii_dirty:  # the staged path wrote every slot of radii_all; the fused path expects zeros (include/sgr.h)
-        if ws.fwd_pending:
-            ws.barrier()
-        ws.radii_all.zero_()
-        ws.barrier()
-        ws.radii_dirty, ws.fwd_pending = False, False
+    ws.radii_dirty = False  # (the fused path needs no particular content of radii_all: it is indexed by slot and rewritten per frame)
     H, W = int(settings.image_height), int(settings.image_width)
     capacity = int(cap.capacity)
     # depth-order slots: learnt from the previous frames (status word 4); the first fused frame compacts into all slots

@@ -409,8 +409,7 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
     st0 = util.settings_from(sgb, frames[0]["cam"], dev)
     wss = SH.PeerWorkspace.emulate(st0, chunk, world, dev)
     for ws in wss:
-        ws.buf[: ws.off_flags].fill_(0x7f)  # poison everything but the barrier pads ...
-        ws.radii_all.zero_()                # ... and radii_all, which the fused forward requires to be zero on entry (include/sgr.h)
+        ws.buf[: ws.off_flags].fill_(0x7f)  # poison everything but the barrier pads: no array needs a particular content on entry
     streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
     for fi, scene in enumerate(frames):
         st = util.settings_from(sgb, scene["cam"], dev)
@@ -442,14 +441,14 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
                     R_r, over, emitted, n_sel, timed_out = (int(v) for v in status[r][:5])
                     assert timed_out == 0, f"{tag}, rank {r}: the device barrier of epoch {timed_out} timed out (ranks not co-scheduled on this GPU)"
                     assert over == 0 and R_r == emitted and R_r <= fst.num_instances, (tag, r, R_r, over, emitted)
-                    assert (n_sel > 0) == compact
+                    assert n_sel > 0
                     n_sel_total += n_sel
                     n_sel_rank[r] = n_sel
                     assert torch.equal(outs[r][3]["radii"][: int(local[r]["means3D"].shape[0])], rad[r * chunk: min(P, (r + 1) * chunk)])
                 imgs = [sum(o[i] for o in outs) for i in range(3)]
                 for a, b, name in zip(imgs, (col, dep, alp), ("color", "depth", "alpha")):
                     assert torch.equal(a, b), f"{tag}: {name} differs from the single-GPU render"
-                if compact:  # each band counts / sorts the Gaussians delivered to it, not all of them
+                if True:  # each band counts / sorts the Gaussians delivered to it, not all of them
                     assert n_sel_total <= world * int((rad > 0).sum()) and (world < 4 or n_sel_total < 0.8 * world * int((rad > 0).sum()))
                 grads = []
                 for r in range(world):
@@ -457,7 +456,6 @@ def test_fused_sharded_step_emulated_ranks(world, compact):
                         grads.append(SH.sharded_backward_raw(st, SH.cyclic_band(H, r, world), wss[r], local[r], int(local[r]["means3D"].shape[0]),
                                                              capacity, outs[r][2], t["grad_color"], t["grad_depth"], t["grad_alpha"]))
                 torch.cuda.synchronize()
-                assert all(int(ws.radii_all.abs().sum()) == 0 for ws in wss), f"{tag}: radii_all must be left zeroed for the next frame"
                 for i, ref in enumerate(ref_grads):
                     if ref is None:
                         assert all(g[i] is None for g in grads)
