@@ -10,7 +10,7 @@
 //              colour/depth grads      sum_p w * dL/dpixel_p
 //              moments                 sum_p q * {1, dx, dy, dx^2, dx dy, dy^2}   -> mean2D.xy, conic, opacity (= Sq / o)
 //              |.| statistic           sum_p |q| (|a dx + b dy| W/2 + |c dy + b dx| H/2)
-//            so each thread walks its chunk of the matrix row (bank-rotated, conflict free) accumulating 11 registers,
+//            so each thread walks its chunk of the matrix row (padded rows, conflict free) accumulating 11 registers,
 //            the 8 chunk-threads of a splat combine with a 3-step butterfly, and 11 global atomics per (tile, splat) leave
 //            the SM — exactly one per component, as in blend_bwd.cu.
 // No per-pair shuffles, selects or shared-memory partial slabs.  Same math as blend_bwd.cu up to summation order.
@@ -22,6 +22,9 @@
 // Also measured (two-barrier kernel, templated on the batch size for the A/B): 16-splat batches at 4 CTAs/SM 640 us, at 5 CTAs/SM (48 registers, 16 B spilled) 718 us,
 // 32-splat batches with 79 registers 615 us, vs 613 us for the default (32 splats, 63 registers, 3 CTAs/SM).  More resident warps buy
 // nothing: the kernel is bound by the NUMBER of instructions it issues (76 % issue-active), not by latency.
+// What did pay (613 -> 550 -> 521 us): cutting instructions.  Phase 2 accumulates the moments in chunk-local integer pixel coordinates
+// (compile-time constants of a fully unrolled loop: 3 FMAs per pixel instead of 8, no coordinate loads, no index rotation — the shared
+// arrays are padded instead) and re-centres them once per thread; phase 1 takes exp() as ex2.approx.
 #include "sgr_common.cuh"
 
 namespace sgr {
@@ -154,7 +157,10 @@ __global__ void __launch_bounds__(256, 3) blend_bwd2_kernel(const FrameDev f, co
 				valid = !(power > 0.0f) && !(power < q1.z);
 				if (valid) {
 					float G;
-					if (kFastExp) {  // A/B only (SGR_BWD2_FASTEXP=1): ex2.approx of power*log2(e), ~4e-7 relative instead of expf's 1 ulp
+					if (kFastExp) {
+						// ex2.approx of power * log2(e): 2 instructions instead of expf's 10 (B200: 550 -> 521 us on config C).  G is ~4e-7
+						// relative off the forward's expf — the same order as the reciprocal below, far inside the 1e-3 gradient bar
+						// (measured vs the reference on configs C / C_s0.05: identical error figures with either).  SGR_BWD2_EXPF=1 selects expf.
 						asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(power * 1.4426950408889634f));
 					} else {
 						G = expf(power);
@@ -293,7 +299,7 @@ cudaError_t launch_blend_bwd2(const FrameDev &f, GeomView g, BinView b, ImgView 
 	if (e != cudaSuccess) return e;
 	const int rows = band_rows(f.band);
 	if (rows <= 0 || f.gx <= 0) return cudaSuccess;
-	static const bool fast_exp = [] { const char *v = getenv("SGR_BWD2_FASTEXP"); return v && atoi(v) == 1; }();
+	static const bool fast_exp = [] { const char *v = getenv("SGR_BWD2_EXPF"); return !(v && atoi(v) == 1); }();
 	static std::atomic<uint64_t> configured{0}, configured_fast{0};
 	count_launch();
 	if (fast_exp) {
