@@ -47,12 +47,24 @@ __device__ __forceinline__ void gather_runs(const PeerTable &pt, const uint32_t 
 	block_run_ranks(rs, mask, pt.world);
 	const uint32_t total = rs.cpre[pt.world];
 	const size_t slot0 = (size_t)pt.rank * (size_t)pt.chunk + (size_t)blockIdx.x * kRunBlock;
-	for (uint32_t base = 0; base < total; base += kRunBlock) {
+	auto fetch = [&](uint32_t base, float4 (&v)[3]) {  // this thread's (up to) three 16-B pieces of the round that starts at `base`
+		const uint32_t n = base < total ? min((uint32_t)kRunBlock, total - base) : 0u;
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const uint32_t e = threadIdx.x + (uint32_t)k * kRunBlock;
+			if (e < 3u * n) {
+				const uint32_t pos = base + e / 3u, part = e % 3u;
+				const int d = run_dest(rs, pos, pt.world);
+				v[k] = reinterpret_cast<const float4 *>(pt.grad2d[d] + (slot0 + (pos - rs.cpre[d])) * 12)[part];
+			}
+		}
+	};
+	auto consume = [&](uint32_t base, const float4 (&v)[3]) {  // collective: publish the round, add the rows that fall into it
 		const uint32_t n = min((uint32_t)kRunBlock, total - base);
-		for (uint32_t e = threadIdx.x; e < 3u * n; e += kRunBlock) {
-			const uint32_t pos = base + e / 3u, part = e % 3u;
-			const int d = run_dest(rs, pos, pt.world);
-			s_g[e] = reinterpret_cast<const float4 *>(pt.grad2d[d] + (slot0 + (pos - rs.cpre[d])) * 12)[part];
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const uint32_t e = threadIdx.x + (uint32_t)k * kRunBlock;
+			if (e < 3u * n) s_g[e] = v[k];
 		}
 		__syncthreads();
 		for (int d = 0; d < pt.world; d++) {
@@ -66,6 +78,15 @@ __device__ __forceinline__ void gather_runs(const PeerTable &pt, const uint32_t 
 			}
 		}
 		__syncthreads();
+	};
+	// rounds of 256 rows, two in flight: the loads of the second are requested before the first is waited for (the typical block has
+	// 1.2-1.4 rows per Gaussian, i.e. exactly two rounds, and one NVLink round trip instead of two was worth 40 us at N = 2)
+	for (uint32_t base = 0; base < total; base += 2u * kRunBlock) {
+		float4 va[3], vb[3];
+		fetch(base, va);
+		fetch(base + kRunBlock, vb);
+		consume(base, va);
+		if (base + kRunBlock < total) consume(base + kRunBlock, vb);
 	}
 }
 

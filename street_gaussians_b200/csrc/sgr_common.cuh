@@ -256,24 +256,23 @@ __device__ __forceinline__ void block_run_ranks(RunScratch &rs, uint32_t mask, i
 		if (lane == 0) rs.wcnt[warp][d] = (uint32_t)__popc(b);
 	}
 	__syncthreads();
-	if ((int)threadIdx.x < world) {
+	if (warp == 0) {  // lane d: exclusive prefix of destination d's hits over the 8 warps, then (shuffles) over the destinations
 		uint32_t run = 0u;
-		for (int w = 0; w < 8; w++) {
-			const uint32_t t = rs.wcnt[w][threadIdx.x];
-			rs.wcnt[w][threadIdx.x] = run;
-			run += t;
+		if (lane < world) {
+			for (int w = 0; w < 8; w++) {
+				const uint32_t t = rs.wcnt[w][lane];
+				rs.wcnt[w][lane] = run;
+				run += t;
+			}
 		}
-		rs.cpre[threadIdx.x + 1] = run;  // count of destination d, turned into a prefix below
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t acc = 0u;
-		rs.cpre[0] = 0u;
-		for (int d = 0; d < world; d++) {
-			const uint32_t c = rs.cpre[d + 1];
-			rs.cpre[d + 1] = acc + c;
-			acc += c;
+		uint32_t incl = run;
+#pragma unroll
+		for (int o = 1; o < kMaxPeers; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
 		}
+		if (lane < world) rs.cpre[lane + 1] = incl;
+		if (lane == 0) rs.cpre[0] = 0u;
 	}
 	__syncthreads();
 }
