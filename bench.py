@@ -142,17 +142,21 @@ def measured_peaks():
 
 
 def ncu_traffic(kernel: str, source: str, workload):
-    """(dram bytes per launch, issue-active %) of `kernel` from profiles/ncu_traffic.json, or (None, None) when the committed capture
-    is for another workload or an older version of the kernel's source file."""
+    """(dram bytes per launch, issue-active %, stale) of `kernel` from profiles/ncu_traffic.json.  The first two are None when the
+    committed capture is for another workload or for another version of the kernel's source file (sha256 of the .cu as of the
+    capture's commit); `stale` then describes that earlier capture so the line can still point at it without claiming it."""
     import hashlib
     try:
         j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
         sha = hashlib.sha256(open(os.path.join(ROOT, "street_gaussians_b200", "csrc", source), "rb").read()).hexdigest()[:16]
         if workload is not None and j.get("workload") == workload and j.get("source_sha16") == sha:
-            return float(j["dram_bytes"]), j.get("issue_active_pct")
+            return float(j["dram_bytes"]), j.get("issue_active_pct"), None
+        return None, None, dict(dram_bytes=float(j["dram_bytes"]), issue_active_pct=j.get("issue_active_pct"), kernel_us=j.get("time_us"),
+                                commit=j.get("commit"), workload=j.get("workload"),
+                                note="ncu capture of an EARLIER build of this kernel (source changed since); not a measurement of this build")
     except Exception:
         pass
-    return None, None
+    return None, None, None
 
 
 def make_settings(mod, cam, dev):
@@ -695,12 +699,14 @@ def main():
         achieved = alg_bytes / (stages["blend_bwd"] * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` capture: only reported when
         # profiles/ncu_traffic.json holds a capture of THIS workload taken from THIS version of the kernel source (sha256 of the .cu)
-        traffic, issue_pct = ncu_traffic("blend_bwd2_kernel", "blend_bwd2.cu", args.workload if not use_dist else None)
+        traffic, issue_pct, traffic_stale = ncu_traffic("blend_bwd2_kernel", "blend_bwd2.cu", args.workload if not use_dist else None)
         roofline = dict(bound="hbm", kernel="blend_bwd2_kernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                         traffic=traffic, issue_active_pct=issue_pct, peak_source=peak_src, algorithmic_bytes=alg_bytes, kernel_ms=stages["blend_bwd"],
-                        note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d; ncu: 76 % issue-active, 1.4 % DRAM): "
-                             "real DRAM traffic is 8x BELOW the algorithmic bytes because the tile lists and records are L2 hits; the HBM "
-                             "fraction is reported as the contract asks; kernel_ms includes the cudaMemsetAsync of the accumulators")
+                        note="blend kernels are FP32/SFU-issue bound, not HBM bound (SURVEY.md §8d; ncu of the round-1 build: 76 % issue-active, "
+                             "1.4 % DRAM): real DRAM traffic is ~8x BELOW the algorithmic bytes because the tile lists and records are L2 hits; "
+                             "the HBM fraction is reported as the contract asks; kernel_ms includes the cudaMemsetAsync of the accumulators")
+        if traffic is None and traffic_stale is not None:
+            roofline["traffic_earlier_build"] = traffic_stale
 
     # ---- end to end from pinned host memory ----
     if args.no_e2e:

@@ -102,10 +102,17 @@ for rep in reps:
         key, src_file = hit
         rd = float(r[ix["dram__bytes_read.sum"]]) * conv.get(units[ix["dram__bytes_read.sum"]], 1.0)
         wr = float(r[ix["dram__bytes_write.sum"]]) * conv.get(units[ix["dram__bytes_write.sum"]], 1.0)
-        sha = hashlib.sha256(open(os.path.join(ROOT, "street_gaussians_b200", "csrc", src_file), "rb").read()).hexdigest()[:16]
+        # the capture belongs to the source as it was when it was taken: SGR_PROFILE_COMMIT names that commit (default: the working tree)
+        commit = os.environ.get("SGR_PROFILE_COMMIT")
+        if commit:
+            blob = subprocess.run(["git", "-C", ROOT, "show", f"{commit}:street_gaussians_b200/csrc/{src_file}"], capture_output=True).stdout
+        else:
+            blob = open(os.path.join(ROOT, "street_gaussians_b200", "csrc", src_file), "rb").read()
+        sha = hashlib.sha256(blob).hexdigest()[:16]
         traffic[key] = dict(workload=workload, source_sha16=sha, dram_bytes=rd + wr, dram_bytes_read=rd, dram_bytes_write=wr,
                             time_us=float(r[ix["gpu__time_duration.sum"]]) * (1e-3 if units[ix["gpu__time_duration.sum"]] in ("ns", "nsecond") else 1.0),
                             issue_active_pct=float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]), capture=os.path.basename(rep),
+                            commit=os.environ.get("SGR_PROFILE_COMMIT", "working tree"),
                             kernel=name[:120])
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 print("wrote profiles/", tag, "and ncu_traffic.json with", sorted(traffic))
