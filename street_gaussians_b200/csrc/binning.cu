@@ -29,7 +29,7 @@ struct GatherCount {
 		return depth_sorted[t] == 0xffffffffu ? 0u : tiles_touched[perm[t]];
 	}
 };
-struct WasDelivered {  // compacted mode: the Gaussians some owner delivered to this rank (radius != 0 <=> its rectangle meets the band)
+struct WasDelivered {  // (predicate of the round-2 second-cut stream compaction; only sizes the temp storage now — the run tables replaced it)
 	const int32_t *radii;
 	__host__ __device__ __forceinline__ bool operator()(int i) const { return radii[i] > 0; }
 };
@@ -101,46 +101,6 @@ cudaError_t launch_count_tiles(const FrameDev &f, GeomView g, const int32_t *rad
 	return cudaGetLastError();
 }
 
-// Compacted mode: tile counts / depth keys of the DELIVERED Gaussians only.  ids[0 .. n_act) are their ascending global ids (ordered
-// stream compaction of radii > 0, so ties in depth still resolve by index); thread j handles ids[j], slots j >= n_act are padding
-// (key 0xFFFFFFFF).  Compared with count_tiles_kernel over all P_total slots (63 us at N = 8, where 85 % of the lanes of every
-// warp idle through the row-span math of the few delivered ones) every lane here has work.  Raises overflow bit 2 when more
-// Gaussians were delivered than there are depth-order slots.
-__global__ void __launch_bounds__(256) count_compact_kernel(const FrameDev f, const GaussRec *__restrict__ rec, const int32_t *__restrict__ radii,
-                                                           const uint32_t *__restrict__ ids, uint32_t *__restrict__ status, const uint32_t cap_v,
-                                                           uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ ckey,
-                                                           uint32_t *__restrict__ cval, float4 *__restrict__ zero_rows) {
-	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t n_act = status[4];
-	if (j == 0 && n_act > cap_v) atomicOr(&status[2], 2u);
-	const bool live = j < n_act && j < cap_v;
-	bool ok = false;
-	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-	CullParams cp = {};
-	float depth = 0.f;
-	uint32_t gidx = 0u;
-	if (live) {
-		gidx = ids[j];
-		const int r = radii[gidx];
-		const float4 q0 = rec[gidx].q0, q1 = rec[gidx].q1;
-		tile_rect(q0.x, q0.y, r, f.gx, f.gy, x0, y0, x1, y1);
-		cp = make_cull(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-		depth = q1.w;
-		ok = true;
-		if (zero_rows) {
-			const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-			zero_rows[3 * (size_t)gidx] = z; zero_rows[3 * (size_t)gidx + 1] = z; zero_rows[3 * (size_t)gidx + 2] = z;
-		}
-	}
-	uint32_t count = 0;
-	visit_tiles<false, uint32_t>(ok, x0, y0, x1, y1, cp, f.band, f.gx, 0u, 0u, nullptr, nullptr, count);
-	if (j < cap_v) {
-		ckey[j] = (live && count > 0u) ? __float_as_uint(depth) : 0xffffffffu;
-		cval[j] = gidx;
-		if (live) tiles_touched[gidx] = count;
-	}
-}
-
 // depth order of the Gaussians + inclusive scan of their instance counts in that order (uncompacted: all f.P Gaussians take part,
 // those without instances carry the key 0xFFFFFFFF and sort to the end).  tiles_touched / depth_key / iota come from
 // preprocess_fwd_kernel<COUNT> or count_tiles_kernel.
@@ -152,39 +112,6 @@ cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st) {
 	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{g.tiles_touched, g.perm, g.depth_sorted});
 	bytes = g.temp_bytes;
 	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, f.P, st);
-}
-
-// Gaussian-sharded forward, from the gathered records to the depth order.
-//   cap_v < 0 : count_tiles_kernel over all f.P slots + the uncompacted depth order;
-//   cap_v >= 0: only the Gaussians delivered to this rank are counted and sorted (`cap_v` depth-order slots).  With N cyclic bands a rank
-//               receives ~1/N .. 2/N of the visible Gaussians; the 4-pass sort over all P was the largest replicated stage of the
-//               round-1 Gaussian-sharded forward (profiles/r01_summary.md §5).  status word 4 = number delivered.
-// *n_order = number of depth-order slots (f.P or cap_v): the emit kernels run over that many.
-cudaError_t launch_count_and_order(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st, int64_t cap_v, float *zero_rows,
-                                   int *n_order) {
-	if (n_order) *n_order = f.P;
-	if (f.P == 0) return cudaSuccess;
-	cudaError_t e;
-	if (cap_v < 0) {
-		if ((e = launch_count_tiles(f, g, radii, st, zero_rows)) != cudaSuccess) return e;
-		return launch_depth_order(f, g, st);
-	}
-	int n = (int)(cap_v < (int64_t)f.P ? cap_v : (int64_t)f.P);
-	if (n < 1) n = 1;
-	size_t bytes = g.temp_bytes;
-	e = cub::DeviceSelect::If(g.temp, bytes, cub::CountingInputIterator<int>(0), g.iota, g.big_count + 4, f.P, WasDelivered{radii}, st);
-	if (e != cudaSuccess) return e;
-	count_launch();
-	count_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, g.rec, radii, g.iota, g.big_count, (uint32_t)n, g.tiles_touched, g.ckey, g.cval,
-	                                                                  reinterpret_cast<float4 *>(zero_rows));
-	if ((e = cudaGetLastError()) != cudaSuccess) return e;
-	bytes = g.temp_bytes;
-	e = cub::DeviceRadixSort::SortPairs(g.temp, bytes, g.ckey, g.depth_sorted, g.cval, g.perm, n, 0, 32, st);
-	if (e != cudaSuccess) return e;
-	if (n_order) *n_order = n;
-	CountIter it(cub::CountingInputIterator<int>(0), GatherCount{g.tiles_touched, g.perm, g.depth_sorted});
-	bytes = g.temp_bytes;
-	return cub::DeviceScan::InclusiveSum(g.temp, bytes, it, g.offsets, n, st);
 }
 
 // ---- fused Gaussian-sharded forward: the delivered runs (sgr_common.cuh "block-run exchange") -> compact depth-sort input ----

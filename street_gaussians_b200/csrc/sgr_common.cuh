@@ -211,7 +211,6 @@ cudaError_t launch_filter(const FrameDev &f, const float *means3D, const float *
                           const float *cov3D_precomp, int32_t *radii, float *means2D, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present, cudaStream_t st);
 cudaError_t launch_depth_order(const FrameDev &f, GeomView g, cudaStream_t st);
-cudaError_t launch_count_and_order(const FrameDev &f, GeomView g, const int32_t *radii, cudaStream_t st, int64_t cap_v, float *zero_rows, int *n_order);
 // fused Gaussian-sharded forward: tile counts + depth order of the runs delivered to this rank (binning.cu)
 cudaError_t launch_count_and_order_runs(const FrameDev &f, GeomView g, int32_t *radii, int world, long long chunk, cudaStream_t st, int64_t cap_v,
                                         float *zero_rows, int *n_order);
