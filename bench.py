@@ -146,6 +146,8 @@ def ncu_traffic(kernel: str, source: str, workload):
     committed capture is for another workload or for another version of the kernel's source file (sha256 of the .cu as of the
     capture's commit); `stale` then describes that earlier capture so the line can still point at it without claiming it."""
     import hashlib
+    if workload is None:  # (multi-GPU runs: the per-rank kernel is a different launch than the captured single-GPU one)
+        return None, None, None
     try:
         j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
         sha = hashlib.sha256(open(os.path.join(ROOT, "street_gaussians_b200", "csrc", source), "rb").read()).hexdigest()[:16]
