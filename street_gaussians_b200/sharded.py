@@ -260,7 +260,6 @@ class PeerWorkspace:
         if _buffers is not None:
             self.buf[self.off_flags:].zero_()
             self.buf[self.off_radii: self.off_grad].zero_()
-        self.radii_dirty = False  # a staged frame (sgr_scatter_records) has written every radius slot since the last fused frame
         self.peers = _capi.SgrPeers()
         self.peers.world, self.peers.rank, self.peers.chunk = self.world, self.rank, self.chunk
         for p in range(self.world):
@@ -375,7 +374,6 @@ class _GaussianShardedRasterize(torch.autograd.Function):
             scatter_records(settings, ws, rec, radii, P)
             ws.barrier()
             ws.fwd_pending = True
-            ws.radii_dirty = True
             st, radii_all, gb, ib = peer_forward_state(ws), ws.radii_all, ws.geom_bytes, ws.img_bytes
         else:
             st, rec_all, gb, ib = alloc_gathered(settings, P_total, S, device)
@@ -529,7 +527,6 @@ def _fused_forward(ctx, tensors, settings, owner, ws: "PeerWorkspace", P: int, c
     cap = owner.capacity
     if not cap.frozen:
         cap.check()
-    ws.radii_dirty = False  # (the fused path needs no particular content of radii_all: it is indexed by slot and rewritten per frame)
     H, W = int(settings.image_height), int(settings.image_width)
     capacity = int(cap.capacity)
     # depth-order slots: learnt from the previous frames (status word 4); the first fused frame compacts into all slots
