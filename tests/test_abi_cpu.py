@@ -158,6 +158,53 @@ def test_instance_capacity_bookkeeping():
     cap.check()              # nothing pending: no-op
 
 
+class _FakeEvent:
+    def __init__(self, done=True):
+        self.done, self.waited = done, False
+
+    def query(self):
+        return self.done
+
+    def synchronize(self):
+        self.waited, self.done = True, True
+
+
+def _status(R, overflow=0, emitted=0, n_sel=0, timed_out=0):
+    return torch.tensor([R, overflow, emitted, n_sel, timed_out, 0, 0, 0], dtype=torch.int32)
+
+
+def test_instance_capacity_async_status_protocol():
+    """InstanceCapacity.check(): frames are examined in submission order once their status has arrived; an overflow raises AFTER the
+    capacity was grown and leaves the later frames pending; the Gaussian capacity of the sharded forward is learnt from
+    status word 4; a barrier timeout is an error; freeze() drains and stops tracking."""
+    cap = sgb.InstanceCapacity(headroom=1.25)
+    cap.observe(10_000)
+    cap.track(_status(9_000, n_sel=2_000), _FakeEvent())
+    late = _FakeEvent(done=False)
+    cap.track(_status(8_000, n_sel=2_100), late)
+    cap.check()                                    # first frame consumed, second not arrived yet
+    assert cap.gaussian_capacity == int(2_000 * 1.25) + 1024 and len(cap._pending) == 1 and not late.waited
+    cap.check(wait=True)
+    assert late.waited and cap.gaussian_capacity == int(2_100 * 1.25) + 1024 and not cap._pending
+    assert len(cap._pool) == 2                      # the pinned words are recycled
+    # overflow of the instance capacity, then of the Gaussian capacity: each reported once, in order, capacity grown first
+    cap.track(_status(50_000, overflow=1, n_sel=2_000), _FakeEvent())
+    cap.track(_status(9_000, overflow=2, n_sel=9_000), _FakeEvent())
+    with pytest.raises(_capi.SgrError, match="instance capacity .* overflowed .*50000"):
+        cap.check()
+    assert cap.capacity == int(50_000 * 1.25) + 4096 and len(cap._pending) == 1
+    with pytest.raises(_capi.SgrError, match="Gaussian capacity .* overflowed .*9000"):
+        cap.check()
+    assert cap.gaussian_capacity == int(9_000 * 1.25) + 1024 and not cap._pending
+    cap.track(_status(100, timed_out=7), _FakeEvent())
+    with pytest.raises(_capi.SgrError, match="barrier of epoch 7 timed out"):
+        cap.check()
+    ev = _FakeEvent(done=False)
+    cap.track(_status(100), ev)
+    assert cap.freeze().frozen and ev.waited and not cap._pending    # freeze() drains what is in flight first
+    assert not cap.freeze(False).frozen
+
+
 def test_header_compiles_as_c_and_struct_layouts_match_ctypes(tmp_path):
     """include/sgr.h is a plain-C header (no C++, no torch types) and EVERY ctypes mirror in _capi.py has the same size and
     field offsets as its C struct — the boundary a cgo / JNI / ctypes binding would be written against."""
